@@ -32,6 +32,7 @@ def _ip(a):
 
 def lu_run(N, v, Px=1, Py=1, Pz=1, n_rep=1, blas_threads=1, want_factors=True):
     """Returns dict(A=[P local arrays], C=[P local arrays], perm, ms, dims)."""
+    N, v, Px, Py, Pz = int(N), int(v), int(Px), int(Py), int(Pz)
     d = layout.dims(N, v, Px, Py, Pz)
     P, loc = d["P"], d["Ml"] * d["Nl"]
     A = np.zeros((P, loc)) if want_factors else None
