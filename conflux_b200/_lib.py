@@ -1,0 +1,69 @@
+"""ctypes binding of libconflux_b200.so (the C ABI declared in include/conflux_b200.h).
+
+The product path fails loudly when the CUDA library is missing or no device is visible -- there is no CPU
+fallback and nothing here imports oracle/."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libconflux_b200.so")
+_lib = None
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+
+
+class ConfluxError(RuntimeError):
+    pass
+
+
+# every exported symbol of include/conflux_b200.h (checked by tests/test_abi.py)
+SYMBOLS = [
+    "cflx_last_error", "cflx_version", "cflx_device_count", "cflx_get_unique_id", "cflx_comm_create",
+    "cflx_comm_barrier", "cflx_comm_destroy", "cflx_auto_grid", "cflx_lu_dims", "cflx_init_matrix_host",
+    "cflx_lu_create", "cflx_lu_info", "cflx_lu_set_local", "cflx_lu_factor", "cflx_lu_get_factors",
+    "cflx_lu_get_permutation", "cflx_lu_launch_count", "cflx_lu_set_profiling", "cflx_lu_phase_ms",
+    "cflx_lu_destroy", "cflx_dbg_gemm_tn", "cflx_dbg_panel", "cflx_dbg_trsm", "cflx_dbg_fp64_peak",
+]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ConfluxError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(conflux_b200 has no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.cflx_last_error.restype = ctypes.c_char_p
+        L.cflx_version.restype = ctypes.c_char_p
+        L.cflx_comm_destroy.restype = None
+        L.cflx_lu_destroy.restype = None
+        L.cflx_comm_destroy.argtypes = [ctypes.c_void_p]
+        L.cflx_lu_destroy.argtypes = [ctypes.c_void_p]
+        L.cflx_comm_barrier.argtypes = [ctypes.c_void_p]
+        L.cflx_comm_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                       ctypes.POINTER(ctypes.c_void_p)]
+        L.cflx_lu_create.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.POINTER(ctypes.c_void_p)]
+        L.cflx_lu_info.argtypes = [ctypes.c_void_p, c_int_p]
+        L.cflx_lu_set_local.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.cflx_lu_factor.argtypes = [ctypes.c_void_p, c_double_p]
+        L.cflx_lu_get_factors.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.cflx_lu_get_permutation.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.cflx_lu_launch_count.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]
+        L.cflx_lu_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.cflx_lu_phase_ms.argtypes = [ctypes.c_void_p, c_double_p]
+        L.cflx_init_matrix_host.argtypes = [ctypes.c_int] * 8 + [ctypes.c_void_p]
+        L.cflx_dbg_gemm_tn.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3 + [ctypes.c_double] * 2 + [
+            ctypes.c_void_p, ctypes.c_int, c_double_p]
+        L.cflx_dbg_panel.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4 + [ctypes.c_int, c_double_p]
+        L.cflx_dbg_trsm.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 5
+        L.cflx_dbg_fp64_peak.argtypes = [ctypes.c_int, c_double_p]
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().cflx_last_error().decode(errors="replace")
+        raise ConfluxError(f"{what} failed with status {rc}: {msg}")

@@ -1,0 +1,238 @@
+// conflux_b200/csrc/dbg.cu -- single-device test / micro-benchmark hooks of the C ABI (cflx_dbg_*).
+// They drive the SAME kernels the factorisation uses, with host buffers in and out, so that tests/ can check every
+// kernel in isolation against numpy / the oracle, and bench.py can time the dominant kernel alone.
+#include <vector>
+
+#include "../../include/conflux_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace cflx;
+
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    int alloc(size_t bytes) {
+        CFLX_CUDA(cudaMalloc(&p, bytes + 4096));
+        return CFLX_OK;
+    }
+    template <class T>
+    T* as() { return (T*)p; }
+};
+int check_device() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_last_error("no CUDA device visible: conflux_b200 has no CPU fallback");
+        return CFLX_ERR_NO_DEVICE;
+    }
+    return CFLX_OK;
+}
+
+// ---- FP64 pipe peak probes ------------------------------------------------------------------------------
+__global__ void dmma_peak_kernel(double* out, int iters) {
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void dfma_peak_kernel(double* out, int iters) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = i;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+extern "C" {
+
+int cflx_dbg_fp64_peak(int which, double* tflops_out) {
+    CFLX_TRY(check_device());
+    int dev = 0, sms = 0;
+    CFLX_CUDA(cudaGetDevice(&dev));
+    CFLX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int threads = 256, blocks = sms * 4, iters = 4096;
+    DevBuf out;
+    CFLX_TRY(out.alloc(sizeof(double) * threads * blocks));
+    cudaEvent_t e0, e1;
+    CFLX_CUDA(cudaEventCreate(&e0));
+    CFLX_CUDA(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CFLX_CUDA(cudaEventRecord(e0));
+        if (which == 0) dmma_peak_kernel<<<blocks, threads>>>(out.as<double>(), iters);
+        else dfma_peak_kernel<<<blocks, threads>>>(out.as<double>(), iters);
+        CFLX_CUDA(cudaEventRecord(e1));
+        CFLX_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        CFLX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        // DMMA 8x8x4 = 256 FMA = 512 flop per warp instruction; DFMA = 2 flop per lane
+        const double flop = which == 0 ? (double)blocks * (threads / 32) * iters * 16 * 512.0
+                                       : (double)blocks * threads * iters * 16 * 2.0;
+        const double tf = flop / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops_out = best;
+    return CFLX_OK;
+}
+
+int cflx_dbg_gemm_tn(int M, int N, int K, const double* AT, const double* B, const double* C, double alpha, double beta,
+                     double* D, int reps, double* ms_out) {
+    CFLX_TRY(check_device());
+    if (M <= 0 || N <= 0 || K <= 0) return CFLX_ERR_ARG;
+    const int64_t ldat = round_up(M, 2), ldb = round_up(N, 2), ldc = ldb;
+    DevBuf dA, dB, dC, dD;
+    CFLX_TRY(dA.alloc(sizeof(double) * K * ldat));
+    CFLX_TRY(dB.alloc(sizeof(double) * K * ldb));
+    CFLX_TRY(dC.alloc(sizeof(double) * M * ldc));
+    CFLX_TRY(dD.alloc(sizeof(double) * M * ldc));
+    CFLX_CUDA(cudaMemset(dA.p, 0, sizeof(double) * K * ldat));
+    CFLX_CUDA(cudaMemset(dB.p, 0, sizeof(double) * K * ldb));
+    CFLX_CUDA(cudaMemcpy2D(dA.p, ldat * 8, AT, (size_t)M * 8, (size_t)M * 8, K, cudaMemcpyHostToDevice));
+    CFLX_CUDA(cudaMemcpy2D(dB.p, ldb * 8, B, (size_t)N * 8, (size_t)N * 8, K, cudaMemcpyHostToDevice));
+    if (C) CFLX_CUDA(cudaMemcpy2D(dC.p, ldc * 8, C, (size_t)N * 8, (size_t)N * 8, M, cudaMemcpyHostToDevice));
+    else CFLX_CUDA(cudaMemset(dC.p, 0, sizeof(double) * M * ldc));
+    GemmArgs g{};
+    g.M = M; g.N = (int)ldb; g.K = K;
+    g.AT = dA.as<double>(); g.ldat = ldat;
+    g.B = dB.as<double>(); g.ldb = ldb;
+    g.C = dC.as<double>(); g.ldc = ldc;
+    g.D = dD.as<double>(); g.ldd = ldc;
+    g.alpha = alpha; g.beta = beta;
+    cudaEvent_t e0, e1;
+    CFLX_CUDA(cudaEventCreate(&e0));
+    CFLX_CUDA(cudaEventCreate(&e1));
+    if (reps < 1) reps = 1;
+    CFLX_TRY(launch_gemm_tn(g, 0));  // warm-up / the result
+    CFLX_CUDA(cudaEventRecord(e0));
+    for (int r = 0; r < reps; ++r) CFLX_TRY(launch_gemm_tn(g, 0));
+    CFLX_CUDA(cudaEventRecord(e1));
+    CFLX_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    CFLX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms_out) *ms_out = ms / reps;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (D) CFLX_CUDA(cudaMemcpy2D(D, (size_t)N * 8, dD.p, ldc * 8, (size_t)N * 8, M, cudaMemcpyDeviceToHost));
+    CFLX_CUDA(cudaDeviceSynchronize());
+    return CFLX_OK;
+}
+
+int cflx_dbg_panel(int n, int v, const double* panel, int* perm_out, double* A00_out, double* LU_out, int reps,
+                   double* ms_out) {
+    CFLX_TRY(check_device());
+    if (n < 0 || v <= 0) return CFLX_ERR_ARG;
+    const int64_t ld = std::max<int64_t>(2, round_up(n, 2));
+    // host transpose into the kernel's K-major layout
+    std::vector<double> WT((size_t)v * ld, 0.0);
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c < v; ++c) WT[(size_t)c * ld + r] = panel[(size_t)r * v + c];
+    DevBuf dW, dW0, dA00, dA00T, dperm;
+    CFLX_TRY(dW.alloc(sizeof(double) * v * ld));
+    CFLX_TRY(dW0.alloc(sizeof(double) * v * ld));
+    CFLX_TRY(dA00.alloc(sizeof(double) * v * v));
+    CFLX_TRY(dA00T.alloc(sizeof(double) * v * v));
+    CFLX_TRY(dperm.alloc(sizeof(int) * 2 * v));
+    CFLX_CUDA(cudaMemcpy(dW0.p, WT.data(), sizeof(double) * v * ld, cudaMemcpyHostToDevice));
+    CFLX_CUDA(cudaMemset(dA00.p, 0, sizeof(double) * v * v));
+    PanelWorkspace ws{};
+    CFLX_TRY(panel_workspace_create(&ws));
+    cudaEvent_t e0, e1;
+    CFLX_CUDA(cudaEventCreate(&e0));
+    CFLX_CUDA(cudaEventCreate(&e1));
+    if (reps < 1) reps = 1;
+    float total = 0;
+    int nb = 0, rc = CFLX_OK;
+    for (int r = 0; r < reps + 1 && rc == CFLX_OK; ++r) {
+        cudaMemcpyAsync(dW.p, dW0.p, sizeof(double) * v * ld, cudaMemcpyDeviceToDevice, 0);
+        cudaEventRecord(e0);
+        rc = launch_panel_getrf_a00(dW.as<double>(), ld, n, v, dperm.as<int>(), dA00.as<double>(), &nb, &ws, 0);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) rc = CFLX_ERR_CUDA;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0) total += ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc == CFLX_OK && n >= v)
+        rc = launch_gather_a00(dW.as<double>(), ld, dperm.as<int>(), v, nb, dA00.as<double>(), dA00T.as<double>(), 0);
+    panel_workspace_destroy(&ws);
+    if (rc != CFLX_OK) {
+        if (rc == CFLX_ERR_CUDA) set_last_error("panel kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return rc;
+    }
+    if (ms_out) *ms_out = total / reps;
+    if (perm_out) CFLX_CUDA(cudaMemcpy(perm_out, dperm.p, sizeof(int) * v, cudaMemcpyDeviceToHost));
+    if (A00_out) CFLX_CUDA(cudaMemcpy(A00_out, dA00.p, sizeof(double) * v * v, cudaMemcpyDeviceToHost));
+    if (LU_out) {
+        CFLX_CUDA(cudaMemcpy(WT.data(), dW.p, sizeof(double) * v * ld, cudaMemcpyDeviceToHost));
+        for (int r = 0; r < n; ++r)
+            for (int c = 0; c < v; ++c) LU_out[(size_t)r * v + c] = WT[(size_t)c * ld + r];
+    }
+    CFLX_CUDA(cudaDeviceSynchronize());
+    return CFLX_OK;
+}
+
+int cflx_dbg_trsm(int n, int v, const double* A00, const double* B, double* X_out, const double* R, double* Y_out) {
+    CFLX_TRY(check_device());
+    if (n <= 0 || v <= 0 || v % 4 != 0) return CFLX_ERR_ARG;
+    int nb = (v % 64 == 0) ? 64 : (v <= 128 ? v : (v % 32 == 0 ? 32 : (v % 16 == 0 ? 16 : 0)));
+    if (nb == 0) return CFLX_ERR_UNSUPPORTED;
+    const int64_t ld = round_up(n, 2);
+    std::vector<double> A00T((size_t)v * v), BT((size_t)v * ld, 0.0), RT((size_t)v * ld, 0.0);
+    for (int i = 0; i < v; ++i)
+        for (int j = 0; j < v; ++j) A00T[(size_t)j * v + i] = A00[(size_t)i * v + j];
+    DevBuf dA, dAT, dUinv, dLinvT, dP, dL, dR, dU;
+    CFLX_TRY(dA.alloc(8 * (size_t)v * v)); CFLX_TRY(dAT.alloc(8 * (size_t)v * v));
+    CFLX_TRY(dUinv.alloc(8 * (size_t)v * v)); CFLX_TRY(dLinvT.alloc(8 * (size_t)v * v));
+    CFLX_TRY(dP.alloc(8 * (size_t)v * ld)); CFLX_TRY(dL.alloc(8 * (size_t)v * ld));
+    CFLX_TRY(dR.alloc(8 * (size_t)v * ld)); CFLX_TRY(dU.alloc(8 * (size_t)v * ld));
+    CFLX_CUDA(cudaMemcpy(dA.p, A00, 8 * (size_t)v * v, cudaMemcpyHostToDevice));
+    CFLX_CUDA(cudaMemcpy(dAT.p, A00T.data(), 8 * (size_t)v * v, cudaMemcpyHostToDevice));
+    CFLX_TRY(launch_diag_inverses(dA.as<double>(), v, nb, dUinv.as<double>(), dLinvT.as<double>(), 0));
+    if (B && X_out) {  // X = B * U^-1, B is n x v row-major
+        for (int r = 0; r < n; ++r)
+            for (int c = 0; c < v; ++c) BT[(size_t)c * ld + r] = B[(size_t)r * v + c];
+        CFLX_CUDA(cudaMemcpy(dP.p, BT.data(), 8 * (size_t)v * ld, cudaMemcpyHostToDevice));
+        CFLX_CUDA(cudaMemset(dL.p, 0, 8 * (size_t)v * ld));
+        CFLX_TRY(trsm_right_upper_T(dA.as<double>(), dUinv.as<double>(), v, nb, dP.as<double>(), dL.as<double>(), ld, n, 0));
+        CFLX_CUDA(cudaMemcpy(BT.data(), dL.p, 8 * (size_t)v * ld, cudaMemcpyDeviceToHost));
+        for (int r = 0; r < n; ++r)
+            for (int c = 0; c < v; ++c) X_out[(size_t)r * v + c] = BT[(size_t)c * ld + r];
+    }
+    if (R && Y_out) {  // Y = L^-1 * R, R is v x n row-major
+        for (int i = 0; i < v; ++i)
+            for (int c = 0; c < n; ++c) RT[(size_t)i * ld + c] = R[(size_t)i * n + c];
+        CFLX_CUDA(cudaMemcpy(dR.p, RT.data(), 8 * (size_t)v * ld, cudaMemcpyHostToDevice));
+        CFLX_CUDA(cudaMemset(dU.p, 0, 8 * (size_t)v * ld));
+        CFLX_TRY(trsm_left_lower_unit(dAT.as<double>(), dLinvT.as<double>(), v, nb, dR.as<double>(), dU.as<double>(), ld,
+                                      (int)ld, 0));
+        CFLX_CUDA(cudaMemcpy(RT.data(), dU.p, 8 * (size_t)v * ld, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < v; ++i)
+            for (int c = 0; c < n; ++c) Y_out[(size_t)i * n + c] = RT[(size_t)i * ld + c];
+    }
+    CFLX_CUDA(cudaDeviceSynchronize());
+    return CFLX_OK;
+}
+
+}  // extern "C"

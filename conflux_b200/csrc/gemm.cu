@@ -1,0 +1,150 @@
+// conflux_b200/csrc/gemm.cu -- FP64 tensor-core GEMM for the trailing-matrix update and the blocked TRSMs.
+//
+//   D[m][n] = beta * C[m][n] + alpha * sum_k AT[k][m] * B[k][n]          (all row-major, "TN" form)
+//
+// Replaces cblas_dgemm at /root/reference/src/conflux/lu/conflux_opt.hpp:1628-1632 (A11 -= A10Rcv * A01Rcv) and,
+// through trsm.cu, the two cblas_dtrsm calls at :1347 and :1539.  Both operands are kept K-MAJOR in HBM
+// (L is stored transposed, L^T[k][row]; U is U[k][col]) so that every operand row a CTA needs is one contiguous
+// 1 KB segment: the producer warp stages tiles with 1-D bulk asynchronous copies (cp.async.bulk -> UBLKCP, the
+// TMA engine) into a 4-stage shared-memory ring guarded by mbarriers, and 8 consumer warps run
+// mma.sync.m8n8k4.f64 (DMMA.8x8x4 -- the native FP64 tensor instruction of sm_100a; tcgen05 has no f64 kind)
+// on 64x32 warp tiles with accumulators in registers.  Shared-memory row stride is 132 doubles (== 4 mod 16) so
+// both fragment loads (lane -> [k = lane&3][outer = lane>>2]) are bank-conflict free per half-warp.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cflx {
+
+namespace {
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, LDT = 132;
+constexpr int NCONS = 8;                    // consumer warps: 2 (m) x 4 (n), warp tile 64 x 32
+constexpr int NTHREADS = (NCONS + 1) * 32;  // + 1 producer warp
+constexpr size_t SMEM_BYTES = (size_t)STAGES * 2 * BK * LDT * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_kernel(GemmArgs g) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* sA = reinterpret_cast<double*>(smem_raw);
+    double* sB = sA + STAGES * BK * LDT;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * BK * LDT);
+    uint64_t* empty = full + STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int KT = (g.K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NCONS);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == NCONS) {
+        // ===== producer: one bulk copy per operand row (lanes 0-15: A rows, 16-31: B rows) =====
+        int wm = g.M - m0;
+        wm = wm > BM ? BM : ((wm + 1) & ~1);
+        int wn = g.N - n0;
+        wn = wn > BN ? BN : ((wn + 1) & ~1);
+        const int rr = lane & 15;
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % STAGES, u = kt / STAGES;
+            if (u > 0) mbar_wait(&empty[s], (u - 1) & 1);
+            const int rows = min(BK, g.K - kt * BK);
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(rows * (wm + wn) * sizeof(double)));
+            __syncwarp();
+            if (rr < rows) {
+                const int64_t k = (int64_t)kt * BK + rr;
+                if (lane < 16)
+                    bulk_g2s(sA + (s * BK + rr) * LDT, g.AT + k * g.ldat + m0, (uint32_t)(wm * sizeof(double)), &full[s]);
+                else
+                    bulk_g2s(sB + (s * BK + rr) * LDT, g.B + k * g.ldb + n0, (uint32_t)(wn * sizeof(double)), &full[s]);
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const int wm_off = (warp >> 2) * 64, wn_off = (warp & 3) * 32;
+    const int g4 = lane >> 2, t4 = lane & 3;
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % STAGES, u = kt / STAGES;
+        mbar_wait(&full[s], u & 1);
+        const double* a_s = sA + s * BK * LDT + wm_off + g4;
+        const double* b_s = sB + s * BK * LDT + wn_off + g4;
+        const int rows = min(BK, g.K - kt * BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            if (kk < rows) {
+                double a[8], b[4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = a_s[(kk + t4) * LDT + 8 * i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = b_s[(kk + t4) * LDT + 8 * j];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+    // ===== epilogue: registers <-> HBM directly, 16-byte accesses (each quad covers one 64 B row segment) =====
+    const double alpha = g.alpha, beta = g.beta;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = m0 + wm_off + 8 * i + g4;
+        if (row >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = n0 + wn_off + 8 * j + 2 * t4;
+            if (col >= g.N) continue;
+            double2 out;
+            out.x = alpha * acc[i][j][0];
+            out.y = alpha * acc[i][j][1];
+            if (beta != 0.0) {
+                const double2 c = *reinterpret_cast<const double2*>(g.C + (int64_t)row * g.ldc + col);
+                out.x += beta * c.x;
+                out.y += beta * c.y;
+            }
+            *reinterpret_cast<double2*>(g.D + (int64_t)row * g.ldd + col) = out;
+        }
+    }
+}
+}  // namespace
+
+int gemm_tn_setup() {
+    static bool done = false;
+    if (!done) {
+        CFLX_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        done = true;
+    }
+    return CFLX_OK;
+}
+
+// Requirements: K % 4 == 0, N even, ldat/ldb/ldc/ldd even, all base pointers 16-byte aligned, ldat >= roundup2(M),
+// ldb >= N.  M may be arbitrary (rows are masked).
+int launch_gemm_tn(const GemmArgs& g, cudaStream_t stream) {
+    if (g.M <= 0 || g.N <= 0 || g.K <= 0) return CFLX_OK;
+    if ((g.K & 3) || (g.N & 1) || (g.ldat & 1) || (g.ldb & 1) || (g.ldc & 1) || (g.ldd & 1)) {
+        set_last_error("gemm_tn: unsupported shape M=%d N=%d K=%d ld=(%lld,%lld,%lld,%lld)", g.M, g.N, g.K,
+                       (long long)g.ldat, (long long)g.ldb, (long long)g.ldc, (long long)g.ldd);
+        return CFLX_ERR_UNSUPPORTED;
+    }
+    CFLX_TRY(gemm_tn_setup());
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
+    gemm_tn_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(g);
+    CFLX_CUDA(cudaGetLastError());
+    return CFLX_OK;
+}
+
+}  // namespace cflx

@@ -1,0 +1,801 @@
+// conflux_b200/csrc/lu.cu -- host orchestration of the CONFLUX LU step loop on B200 + the C ABI.
+//
+// One rank = one GPU = one host thread/process (SPMD, like the reference's MPI ranks).  The step order follows
+// conflux::LU_rep<T> (/root/reference/src/conflux/lu/conflux_opt.hpp:535-1803, blueprint in SURVEY.md appendix A)
+// but the data layout and the division of labour are B200-first:
+//   * A11 stays resident in HBM (row-major Ml x Nl, 64-bit indexing); L and U are written IN PLACE into it
+//     (the reference keeps a second Ml x Nl array A10resultBuff + a caller-owned C and MPI_Puts into it);
+//   * panels are kept transposed/K-major (see gemm.cu, panel.cu) so every kernel streams contiguous rows;
+//   * pivot rows are gathered by ONE sum-reduction over the (i,k) plane of zero-padded v x ncols buffers
+//     (exact: every row has exactly one non-zero contributor per layer) instead of reduce + p2p gather
+//     (conflux_opt.hpp:1164-1173,1226-1258,1474-1511); A00 and the pivot ids travel in one broadcast
+//     (conflux_opt.hpp:818-850,872);
+//   * all communication is NCCL on the rank's stream; at Px == 1 the whole factorisation is enqueued without a
+//     single host synchronisation, at Px > 1 the host reads back one int (this rank's pivot count) per step.
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "../../include/conflux_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cflx {
+static thread_local char g_err[1024] = "";
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace cflx
+
+using namespace cflx;
+
+#define CFLX_NCCL(call)                                                                            \
+    do {                                                                                           \
+        ncclResult_t r__ = (call);                                                                 \
+        if (r__ != ncclSuccess) {                                                                  \
+            set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(r__)); \
+            return CFLX_ERR_NCCL;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+struct cflx_comm {
+    int world_size = 1, world_rank = 0, device = 0;
+    ncclComm_t world = nullptr;
+    cudaStream_t stream = nullptr;
+    double* d_scratch = nullptr;  // 1 double for barriers
+};
+
+namespace {
+struct SubComm {
+    ncclComm_t c = nullptr;
+    int size = 1, rank = 0;
+};
+
+enum Phase { PH_PANEL = 0, PH_TOURN, PH_MOVES, PH_REDUCE, PH_TRSM, PH_GEMM, PH_STORE, PH_OTHER, PH_COUNT };
+
+int flipbit(int n, int k) { return n ^ (1 << k); }
+int butterfly_pair(int pi, int r, int Px) {  // conflux_opt.cpp:59-72
+    int src = flipbit(pi, r);
+    if (src >= Px) {
+        if (r == 0) src = pi;
+        else {
+            src = flipbit(src, r - 1);
+            if (src >= Px) src = Px - 1;
+        }
+    }
+    return src;
+}
+int pick_nb(int v) {
+    if (v % 64 == 0) return 64;
+    if (v <= 128) return v;
+    if (v % 32 == 0) return 32;
+    if (v % 16 == 0) return 16;
+    return 0;
+}
+}  // namespace
+
+struct cflx_lu {
+    cflx_comm* comm = nullptr;
+    int M = 0, N = 0, v = 0, Px = 1, Py = 1, Pz = 1, P = 1, Ml = 0, Nl = 0, Nt = 0, Mt = 0, nlayr = 0;
+    int pi = 0, pj = 0, pk = 0, rank = 0, nb = 0;
+    SubComm k_comm, i_comm, jk_comm, ik_comm;
+    // device memory
+    double *A0 = nullptr, *A11 = nullptr, *PT = nullptr, *PT2 = nullptr, *W = nullptr, *LT = nullptr, *A01raw = nullptr,
+           *U = nullptr, *tmp = nullptr, *A00 = nullptr, *A00T = nullptr, *Uinv = nullptr, *LinvT = nullptr,
+           *candH = nullptr, *S = nullptr, *W2 = nullptr, *bcast = nullptr, *Cbuf = nullptr, *xbuf = nullptr;
+    int *gri = nullptr, *gri_tmp = nullptr, *igri = nullptr, *perm = nullptr, *gpivots = nullptr, *tagsH = nullptr,
+        *tagsS = nullptr, *hist = nullptr, *plan_mem = nullptr, *idx_buf = nullptr;
+    MovePlan plan{};
+    PanelWorkspace pws{};
+    int64_t ldp_max = 0;
+    int* h_npiv = nullptr;  // pinned
+    std::vector<int> h_hist;
+    bool have_input = false, factored = false, profiling = false;
+    int64_t launches = 0;
+    double phase_ms[PH_COUNT] = {0};
+    std::vector<cudaEvent_t> ev;
+};
+
+namespace {
+
+template <class T>
+int dmalloc(T** p, size_t n) {
+    CFLX_CUDA(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T) + 4096));  // tail pad: bulk copies may over-read
+    return CFLX_OK;
+}
+
+int make_sub(cflx_comm* c, int color, int key, int size, SubComm* out) {
+    out->size = size;
+    out->rank = key;
+    out->c = nullptr;
+    if (c->world_size == 1) return CFLX_OK;
+    // every rank takes part in every split (collective over the world communicator)
+    CFLX_NCCL(ncclCommSplit(c->world, color, key, &out->c, nullptr));
+    int r = -1, s = -1;
+    CFLX_NCCL(ncclCommUserRank(out->c, &r));
+    CFLX_NCCL(ncclCommCount(out->c, &s));
+    if (r != key || s != size) {
+        set_last_error("sub-communicator mismatch: rank %d/%d expected %d/%d", r, s, key, size);
+        return CFLX_ERR_NCCL;
+    }
+    return CFLX_OK;
+}
+
+struct PhaseTimer {
+    cflx_lu* lu;
+    int ph;
+    cudaEvent_t a = nullptr, b = nullptr;
+    PhaseTimer(cflx_lu* l, int p) : lu(l), ph(p) {
+        if (lu->profiling) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, lu->comm->stream);
+        }
+    }
+    ~PhaseTimer() {
+        if (lu->profiling) {
+            cudaEventRecord(b, lu->comm->stream);
+            cudaEventSynchronize(b);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, a, b);
+            lu->phase_ms[ph] += ms;
+            cudaEventDestroy(a);
+            cudaEventDestroy(b);
+        }
+    }
+};
+
+// exchange of tournament candidates with the butterfly partner(s) of round r (conflux_opt.hpp:242-280)
+int tournament_exchange(cflx_lu* lu, int r, int my_half, cudaStream_t s) {
+    const int v = lu->v, Px = lu->Px, pi = lu->pi;
+    const int src = butterfly_pair(pi, r, Px);
+    const int other = 1 - my_half;
+    const size_t hv = (size_t)v * v;
+    double* mine = lu->candH + my_half * hv;
+    double* recv = lu->candH + other * hv;
+    int* mine_t = lu->tagsH + my_half * v;
+    int* recv_t = lu->tagsH + other * v;
+    if (src == pi) {  // MPI_Sendrecv with itself: the own half is duplicated into the other half
+        CFLX_CUDA(cudaMemcpyAsync(recv, mine, hv * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        CFLX_CUDA(cudaMemcpyAsync(recv_t, mine_t, v * sizeof(int), cudaMemcpyDeviceToDevice, s));
+        return CFLX_OK;
+    }
+    CFLX_NCCL(ncclGroupStart());
+    for (int ppi = 0; ppi < Px; ++ppi) {
+        if (ppi == pi || butterfly_pair(ppi, r, Px) != pi) continue;
+        // mutual partner gets my own half; a one-sided requester gets the lower half (the reference's extra Isend)
+        const bool mutual = (ppi == src);
+        const double* sv = mutual ? mine : lu->candH + hv;
+        const int* st = mutual ? mine_t : lu->tagsH + v;
+        CFLX_NCCL(ncclSend(sv, hv, ncclDouble, ppi, lu->i_comm.c, s));
+        CFLX_NCCL(ncclSend(st, v, ncclInt, ppi, lu->i_comm.c, s));
+    }
+    CFLX_NCCL(ncclRecv(recv, hv, ncclDouble, src, lu->i_comm.c, s));
+    CFLX_NCCL(ncclRecv(recv_t, v, ncclInt, src, lu->i_comm.c, s));
+    CFLX_NCCL(ncclGroupEnd());
+    return CFLX_OK;
+}
+
+// S[c][h*v + i] = candH[h][c][i]; tagsS likewise
+__global__ void stack_kernel(const double* __restrict__ candH, const int* __restrict__ tagsH, int v, double* __restrict__ S,
+                             double* __restrict__ W2, int* __restrict__ tagsS) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t tot = (int64_t)2 * v * v;
+    if (e < tot) {
+        const int c = (int)(e / (2 * v)), hi = (int)(e % (2 * v));
+        const int h = hi / v, i = hi % v;
+        const double x = candH[(size_t)h * v * v + (size_t)c * v + i];
+        S[e] = x;
+        W2[e] = x;
+    }
+    if (e < 2 * v) tagsS[e] = tagsH[e];
+}
+__global__ void gather_rows_kernel(const double* __restrict__ A, int64_t lda, const int* __restrict__ src_rows, int nrows,
+                                   int ncols, double* __restrict__ out) {
+    const int i = blockIdx.y;
+    if (i >= nrows) return;
+    const double* s = A + (int64_t)src_rows[i] * lda;
+    double* d = out + (int64_t)i * ncols;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += gridDim.x * blockDim.x) d[c] = s[c];
+}
+__global__ void scatter_rows_kernel(const double* __restrict__ in, int ncols, const int* __restrict__ dst_rows, int nrows,
+                                    double* __restrict__ C, int64_t ldc) {
+    const int i = blockIdx.y;
+    if (i >= nrows) return;
+    const double* s = in + (int64_t)i * ncols;
+    double* d = C + (int64_t)dst_rows[i] * ldc;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += gridDim.x * blockDim.x) d[c] = s[c];
+}
+
+int lu_step(cflx_lu* lu, int k, int& fnpr) {
+    cudaStream_t s = lu->comm->stream;
+    const int v = lu->v, Px = lu->Px, Py = lu->Py, Pz = lu->Pz, Ml = lu->Ml, Nl = lu->Nl;
+    const int pi = lu->pi, pj = lu->pj, pk = lu->pk;
+    const int loff = (k / Py) * v, pjk = k % Py, pik = k % Px;
+    const bool on_col = (pj == pjk), on_row = (pi == pik), layer0 = (pk == 0);
+    const int c0 = loff + (pj <= pjk ? v : 0);  // first live column of this rank after step k
+    const int ncols = Nl - c0;
+    const int fnpr_old = fnpr;
+    const int n_old = Ml - fnpr_old;
+    const int64_t ldk = std::max<int64_t>(2, round_up(n_old, 2));
+    int nR = 0;
+    while ((1 << nR) < Px) ++nR;
+
+    // ---- step 0: panel extract (+ reduce over layers onto pk = 0)            conflux_opt.hpp:618-648
+    if (on_col) {
+        PhaseTimer t(lu, PH_PANEL);
+        CFLX_TRY(launch_extract_panel_T(lu->A11, Nl, fnpr_old, loff, n_old, v, lu->PT, ldk, s));
+        lu->launches++;
+        if (Pz > 1 && n_old > 0)
+            CFLX_NCCL(ncclReduce(lu->PT, lu->PT, (size_t)v * ldk, ncclDouble, ncclSum, 0, lu->k_comm.c, s));
+    }
+    // ---- step 1: local pivot search + tournament on column pj == k % Py, layer 0   conflux_opt.hpp:693-816
+    if (on_col && layer0) {
+        int my_half = 0;
+        {
+            PhaseTimer t(lu, PH_PANEL);
+            CFLX_CUDA(cudaMemcpyAsync(lu->W, lu->PT, (size_t)v * ldk * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            int nb_used = 0;
+            if (nR == 0) {  // the local search already is the tournament: A00 comes from it
+                CFLX_TRY(launch_panel_getrf_a00(lu->W, ldk, n_old, v, lu->perm, lu->A00, &nb_used, &lu->pws, s));
+                CFLX_TRY(launch_gather_a00(lu->W, ldk, lu->perm, v, nb_used, lu->A00, lu->A00T, s));
+                lu->launches += 2;
+            } else {
+                CFLX_TRY(launch_panel_getrf(lu->W, ldk, n_old, v, lu->perm, &lu->pws, s));
+                lu->launches++;
+            }
+            int first_partner = flipbit(pi, 0);
+            if (first_partner > Px - 1) first_partner = Px - 1;
+            my_half = first_partner < pi ? 1 : 0;  // "higher rank puts his candidates below" (conflux_opt.hpp:717-750)
+            CFLX_TRY(launch_gather_winners(lu->PT, ldk, lu->gri + fnpr_old, n_old, lu->perm, v,
+                                           lu->candH + (size_t)my_half * v * v, v, lu->tagsH + my_half * v, 0, s));
+            lu->launches++;
+        }
+        PhaseTimer t(lu, PH_TOURN);
+        for (int r = 0; r < nR; ++r) {
+            CFLX_TRY(tournament_exchange(lu, r, my_half, s));
+            const int64_t tot = (int64_t)2 * v * v;
+            stack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(lu->candH, lu->tagsH, v, lu->S, lu->W2, lu->tagsS);
+            CFLX_CUDA(cudaGetLastError());
+            const bool last = (r == nR - 1);
+            int nb_used = 0;
+            if (last) {
+                CFLX_TRY(launch_panel_getrf_a00(lu->W2, 2 * v, 2 * v, v, lu->perm, lu->A00, &nb_used, &lu->pws, s));
+                CFLX_TRY(launch_gather_a00(lu->W2, 2 * v, lu->perm, v, nb_used, lu->A00, lu->A00T, s));
+                lu->launches++;
+                my_half = 0;
+            } else {
+                CFLX_TRY(launch_panel_getrf(lu->W2, 2 * v, 2 * v, v, lu->perm, &lu->pws, s));
+                my_half = butterfly_pair(pi, r + 1, Px) < pi ? 1 : 0;
+            }
+            CFLX_TRY(launch_gather_winners(lu->S, 2 * v, lu->tagsS, 2 * v, lu->perm, v,
+                                           lu->candH + (size_t)my_half * v * v, v, lu->tagsH + my_half * v, 0, s));
+            lu->launches += 3;
+        }
+        // winners now sit in the upper half: tagsH[0..v) = global pivot rows (conflux_opt.hpp:810-815)
+    }
+    // ---- A00 + pivot ids to everybody (one broadcast)                     conflux_opt.hpp:818-850,872
+    {
+        PhaseTimer t(lu, PH_TOURN);
+        if (lu->P > 1) {
+            const int root = (pik * Py + pjk) * Pz;  // rank of (k % Px, k % Py, 0)
+            if (lu->rank == root) {
+                CFLX_TRY(launch_pack_bcast(lu->A00, lu->tagsH, v, lu->bcast, s));
+                lu->launches++;
+            }
+            CFLX_NCCL(ncclBroadcast(lu->bcast, lu->bcast, (size_t)v * v + v, ncclDouble, root, lu->comm->world, s));
+            CFLX_TRY(launch_unpack_bcast(lu->bcast, v, lu->A00, lu->A00T, lu->gpivots, s));
+            lu->launches++;
+        } else {
+            CFLX_CUDA(cudaMemcpyAsync(lu->gpivots, lu->tagsH, v * sizeof(int), cudaMemcpyDeviceToDevice, s));
+        }
+        CFLX_TRY(launch_record_pivots(lu->gpivots, v, lu->hist, k, s));
+        lu->launches++;
+    }
+    // ---- step 2: localise pivots, push them up, extract pivot rows        conflux_opt.hpp:876-1147
+    int npiv = v;
+    {
+        PhaseTimer t(lu, PH_MOVES);
+        CFLX_TRY(launch_plan_moves(lu->gpivots, v, Px, pi, fnpr_old, Ml, lu->igri, lu->plan, s));
+        lu->launches++;
+        if (Px > 1) {
+            CFLX_CUDA(cudaMemcpyAsync(lu->h_npiv, lu->plan.npiv, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CFLX_CUDA(cudaStreamSynchronize(s));
+            npiv = *lu->h_npiv;
+        }
+        if (npiv < 0 || npiv > v || fnpr_old + npiv > Ml) {
+            set_last_error("step %d: inconsistent pivot count %d (fnpr %d, Ml %d)", k, npiv, fnpr_old, Ml);
+            return CFLX_ERR_STATE;
+        }
+        const int col_lo = layer0 ? 0 : loff;
+        const int64_t ldu = std::max(2, ncols);
+        if (ncols > 0 || npiv > 0) {
+            CFLX_TRY(launch_push_phase1(lu->A11, Nl, Nl, col_lo, lu->plan, v, lu->tmp, ncols > 0 ? lu->A01raw : nullptr, ldu,
+                                        c0, s));
+            CFLX_TRY(launch_push_phase2(lu->A11, Nl, Nl, col_lo, lu->plan, v, s));
+            CFLX_TRY(launch_push_phase3(lu->A11, Nl, Nl, col_lo, fnpr_old, lu->plan, v, lu->tmp, s));
+            lu->launches += 3;
+        }
+        CFLX_TRY(launch_update_gri(lu->gri, lu->gri_tmp, lu->igri, lu->plan.rowsrc, fnpr_old, Ml, v, Px, s));
+        lu->launches += 2;
+    }
+    fnpr = fnpr_old + npiv;
+    const int n_act = Ml - fnpr;
+    const int64_t ld2 = std::max<int64_t>(2, round_up(n_act, 2));
+    const int64_t ldu = std::max(2, ncols);
+    if (on_col && layer0 && n_act > 0) {
+        PhaseTimer t(lu, PH_MOVES);
+        CFLX_TRY(launch_compact_panel(lu->PT, ldk, lu->PT2, ld2, lu->plan.rowsrc, fnpr_old, lu->plan.npiv, Ml, v, s));
+        lu->launches++;
+    }
+    // ---- steps 2b/3: pivot rows summed over layers and gathered on row pi == k % Px   conflux_opt.hpp:1164-1260
+    if (ncols > 0 && Px * Pz > 1) {
+        PhaseTimer t(lu, PH_REDUCE);
+        CFLX_NCCL(ncclReduce(lu->A01raw, lu->A01raw, (size_t)v * ldu, ncclDouble, ncclSum, pik * Pz, lu->ik_comm.c, s));
+    }
+    // ---- steps 4/5: the two triangular solves                              conflux_opt.hpp:1329-1359,1522-1551
+    if (layer0 && (on_col || on_row)) {
+        PhaseTimer t(lu, PH_TRSM);
+        CFLX_TRY(launch_diag_inverses(lu->A00, v, lu->nb, lu->Uinv, lu->LinvT, s));
+        lu->launches++;
+    }
+    if (on_col && layer0 && n_act > 0) {
+        {
+            PhaseTimer t(lu, PH_TRSM);
+            CFLX_TRY(trsm_right_upper_T(lu->A00, lu->Uinv, v, lu->nb, lu->PT2, lu->LT, ld2, n_act, s));
+            lu->launches += 2 * (v / lu->nb) - 1;
+        }
+        PhaseTimer t(lu, PH_STORE);
+        CFLX_TRY(launch_store_panel_T(lu->A11, Nl, fnpr, loff, n_act, v, lu->LT, ld2, s));  // L in place
+        lu->launches++;
+    }
+    if (Py * Pz > 1 && n_act > 0) {  // L panel to every (pj', pk') of my grid row    conflux_opt.hpp:1404-1434
+        PhaseTimer t(lu, PH_REDUCE);
+        CFLX_NCCL(ncclBroadcast(lu->LT, lu->LT, (size_t)v * ld2, ncclDouble, pjk * Pz, lu->jk_comm.c, s));
+    }
+    if (on_row && layer0 && ncols > 0) {
+        PhaseTimer t(lu, PH_TRSM);
+        CFLX_TRY(trsm_left_lower_unit(lu->A00T, lu->LinvT, v, lu->nb, lu->A01raw, lu->U, ldu, ncols, s));
+        lu->launches += 2 * (v / lu->nb) - 1;
+    }
+    if (Px * Pz > 1 && ncols > 0) {  // U panel to every (pi', pk') of my grid column   conflux_opt.hpp:1567-1593
+        PhaseTimer t(lu, PH_REDUCE);
+        CFLX_NCCL(ncclBroadcast(lu->U, lu->U, (size_t)v * ldu, ncclDouble, pik * Pz, lu->ik_comm.c, s));
+    }
+    if (layer0) {  // factor storage: my promoted rows receive their U part and diagonal block   :1721-1754
+        PhaseTimer t(lu, PH_STORE);
+        if (ncols > 0) {
+            CFLX_TRY(launch_store_u_rows(lu->A11, Nl, fnpr_old, lu->plan, lu->U, ldu, c0, ncols, v, s));
+            lu->launches++;
+        }
+        if (on_col) {
+            CFLX_TRY(launch_store_diag(lu->A11, Nl, fnpr_old, lu->plan, lu->A00, loff, v, s));
+            lu->launches++;
+        }
+    }
+    // ---- step 6: trailing update on every rank and layer                    conflux_opt.hpp:1628-1632
+    if (n_act > 0 && ncols > 0) {
+        PhaseTimer t(lu, PH_GEMM);
+        GemmArgs g{};
+        g.M = n_act;
+        g.N = ncols;
+        g.K = lu->nlayr;
+        g.AT = lu->LT + (int64_t)pk * lu->nlayr * ld2;
+        g.ldat = ld2;
+        g.B = lu->U + (int64_t)pk * lu->nlayr * ldu;
+        g.ldb = ldu;
+        g.C = lu->A11 + (int64_t)fnpr * Nl + c0;
+        g.ldc = Nl;
+        g.D = lu->A11 + (int64_t)fnpr * Nl + c0;
+        g.ldd = Nl;
+        g.alpha = -1.0;
+        g.beta = 1.0;
+        CFLX_TRY(launch_gemm_tn(g, s));
+        lu->launches++;
+    }
+    return CFLX_OK;
+}
+
+int grid_barrier(cflx_comm* c) {
+    if (c->world_size > 1)
+        CFLX_NCCL(ncclAllReduce(c->d_scratch, c->d_scratch, 1, ncclDouble, ncclSum, c->world, c->stream));
+    CFLX_CUDA(cudaStreamSynchronize(c->stream));
+    return CFLX_OK;
+}
+
+void free_lu(cflx_lu* lu) {
+    if (!lu) return;
+    cudaSetDevice(lu->comm->device);
+    double* dbl[] = {lu->A0, lu->A11, lu->PT, lu->PT2, lu->W, lu->LT, lu->A01raw, lu->U, lu->tmp, lu->A00, lu->A00T,
+                     lu->Uinv, lu->LinvT, lu->candH, lu->S, lu->W2, lu->bcast, lu->Cbuf, lu->xbuf};
+    for (double* p : dbl) cudaFree(p);
+    int* ints[] = {lu->gri, lu->gri_tmp, lu->igri, lu->perm, lu->gpivots, lu->tagsH, lu->tagsS, lu->hist, lu->plan_mem,
+                   lu->idx_buf};
+    for (int* p : ints) cudaFree(p);
+    if (lu->h_npiv) cudaFreeHost(lu->h_npiv);
+    if (lu->pws.slot_flag) panel_workspace_destroy(&lu->pws);
+    for (SubComm* sc : {&lu->k_comm, &lu->i_comm, &lu->jk_comm, &lu->ik_comm})
+        if (sc->c) ncclCommDestroy(sc->c);
+    delete lu;
+}
+}  // namespace
+
+// ======================================================================================================== C ABI
+extern "C" {
+
+const char* cflx_last_error(void) { return g_err; }
+const char* cflx_version(void) { return "conflux_b200 0.1 (sm_100a)"; }
+
+int cflx_device_count(int* count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        n = 0;
+        cudaGetLastError();
+    }
+    *count = n;
+    return CFLX_OK;
+}
+
+int cflx_get_unique_id(void* id_out) {
+    static_assert(sizeof(ncclUniqueId) == CFLX_UNIQUE_ID_BYTES, "unique id size");
+    ncclUniqueId id;
+    CFLX_NCCL(ncclGetUniqueId(&id));
+    std::memcpy(id_out, &id, sizeof(id));
+    return CFLX_OK;
+}
+
+int cflx_comm_create(int world_size, int world_rank, const void* unique_id, int device, cflx_comm** out) {
+    if (!out || world_size < 1 || world_rank < 0 || world_rank >= world_size) return CFLX_ERR_ARG;
+    int ndev = 0;
+    cflx_device_count(&ndev);
+    if (ndev == 0) {
+        set_last_error("no CUDA device visible: conflux_b200 has no CPU fallback");
+        return CFLX_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) {
+        set_last_error("device %d out of range (%d visible)", device, ndev);
+        return CFLX_ERR_ARG;
+    }
+    CFLX_CUDA(cudaSetDevice(device));
+    auto* c = new cflx_comm;
+    c->world_size = world_size;
+    c->world_rank = world_rank;
+    c->device = device;
+    CFLX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CFLX_CUDA(cudaMalloc((void**)&c->d_scratch, sizeof(double)));
+    CFLX_CUDA(cudaMemset(c->d_scratch, 0, sizeof(double)));
+    if (world_size > 1) {
+        if (!unique_id) {
+            set_last_error("unique_id required for world_size > 1");
+            return CFLX_ERR_ARG;
+        }
+        ncclUniqueId id;
+        std::memcpy(&id, unique_id, sizeof(id));
+        CFLX_NCCL(ncclCommInitRank(&c->world, world_size, id, world_rank));
+    }
+    *out = c;
+    return CFLX_OK;
+}
+
+int cflx_comm_barrier(cflx_comm* c) {
+    if (!c) return CFLX_ERR_ARG;
+    CFLX_CUDA(cudaSetDevice(c->device));
+    return grid_barrier(c);
+}
+
+void cflx_comm_destroy(cflx_comm* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->world) ncclCommDestroy(c->world);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    cudaFree(c->d_scratch);
+    delete c;
+}
+
+int cflx_auto_grid(int M, int N, int P, int* Px, int* Py, int* Pz) {  // lu_params.hpp:21-47
+    if (M <= 0 || N <= 0 || P <= 0) return CFLX_ERR_ARG;
+    const double ratio = 1.0 * std::max(M, N) / std::min(M, N);
+    const int p1 = (int)std::cbrt(P / ratio);
+    const int psq = (int)std::sqrt(P / ratio);
+    const int phs = (int)std::sqrt(P / (2 * ratio));
+    if (P == psq * psq) {
+        *Px = psq; *Py = psq; *Pz = 1;
+        return CFLX_OK;
+    }
+    if (phs * phs == P / 2) {
+        *Px = phs; *Py = phs; *Pz = 2;
+        return CFLX_OK;
+    }
+    int d[3] = {p1, (int)(ratio * p1), 0};
+    d[2] = P / (d[0] * d[1]);
+    std::sort(d, d + 3, [](int a, int b) { return a > b; });
+    *Px = d[0]; *Py = d[1]; *Pz = d[2];
+    return CFLX_OK;
+}
+
+int cflx_lu_dims(int M, int N, int v, int Px, int Py, int Pz, int* o) {  // lu_params.hpp:67-82
+    if (M <= 0 || N <= 0 || v <= 0 || Px <= 0 || Py <= 0 || Pz <= 0 || !o) return CFLX_ERR_ARG;
+    const int tx = (int)std::ceil((double)M / (v * Px)), ty = (int)std::ceil((double)N / (v * Py));
+    const int Mp = v * Px * tx, Np = v * Py * ty;
+    const int Nt = (int)std::ceil((double)Np / v), Mt = (int)std::ceil((double)Mp / v);
+    o[0] = Mp; o[1] = Np;
+    o[2] = (int)std::ceil((double)Mt / Px) * v;
+    o[3] = (int)std::ceil((double)Nt / Py) * v;
+    o[4] = Nt; o[5] = (v + Pz - 1) / Pz; o[6] = Mt; o[7] = Px * Py * Pz;
+    return CFLX_OK;
+}
+
+int cflx_init_matrix_host(int M, int N, int v, int Px, int Py, int Pz, int rank, int seed, double* out) {
+    int d[8];
+    CFLX_TRY(cflx_lu_dims(M, N, v, Px, Py, Pz, d));
+    const int Ml = d[2], Nl = d[3];
+    if (rank < 0 || rank >= d[7] || !out) return CFLX_ERR_ARG;
+    std::fill(out, out + (size_t)Ml * Nl, 0.0);
+    if (rank % Pz != 0) return CFLX_OK;  // layers pk != 0 start at zero (lu_params.hpp:149-155)
+    // lu_params.hpp:364-375: mt19937_64(seed + rank), values 5 + U[0,1), tile by tile (lti outer, ltj inner),
+    // row-major inside a tile (libs/costa/src/costa/grid2grid/grid_layout.hpp:68-92)
+    std::mt19937_64 eng((unsigned long long)(seed + rank));
+    std::uniform_real_distribution<double> dist;
+    for (int lti = 0; lti < Ml / v; ++lti)
+        for (int ltj = 0; ltj < Nl / v; ++ltj)
+            for (int li = 0; li < v; ++li)
+                for (int lj = 0; lj < v; ++lj) out[(size_t)(lti * v + li) * Nl + ltj * v + lj] = 5 + dist(eng);
+    return CFLX_OK;
+}
+
+int cflx_lu_create(cflx_comm* c, int M, int N, int v, int Px, int Py, int Pz, cflx_lu** out) {
+    if (!c || !out || M <= 0 || N <= 0 || v <= 0) return CFLX_ERR_ARG;
+    CFLX_CUDA(cudaSetDevice(c->device));
+    if (Px <= 0 || Py <= 0 || Pz <= 0) CFLX_TRY(cflx_auto_grid(M, N, c->world_size, &Px, &Py, &Pz));
+    if (Px != Py) {
+        set_last_error("grid %dx%dx%d: the CONFLUX LU path requires Px == Py (SURVEY.md fact 6)", Px, Py, Pz);
+        return CFLX_ERR_UNSUPPORTED;
+    }
+    if (Px * Py * Pz != c->world_size) {
+        set_last_error("grid %dx%dx%d does not match the %d ranks of the communicator", Px, Py, Pz, c->world_size);
+        return CFLX_ERR_ARG;
+    }
+    if (v % 4 != 0 || v % Pz != 0 || (v / Pz) % 4 != 0 || pick_nb(v) == 0) {
+        set_last_error("tile size v=%d unsupported: need v %% 4 == 0, (v / Pz) %% 4 == 0 and v <= 128 or v %% 16 == 0", v);
+        return CFLX_ERR_UNSUPPORTED;
+    }
+    int d[8];
+    CFLX_TRY(cflx_lu_dims(M, N, v, Px, Py, Pz, d));
+    auto* lu = new cflx_lu;
+    lu->comm = c;
+    lu->M = d[0]; lu->N = d[1]; lu->Ml = d[2]; lu->Nl = d[3]; lu->Nt = d[4]; lu->nlayr = d[5]; lu->Mt = d[6]; lu->P = d[7];
+    lu->v = v; lu->Px = Px; lu->Py = Py; lu->Pz = Pz;
+    lu->rank = c->world_rank;  // row-major cart numbering: rank = (pi*Py + pj)*Pz + pk
+    lu->pi = lu->rank / (Py * Pz);
+    lu->pj = (lu->rank / Pz) % Py;
+    lu->pk = lu->rank % Pz;
+    lu->nb = pick_nb(v);
+    if (lu->M != lu->N) {
+        set_last_error("only square matrices are supported (the miniapp passes M = N)");
+        delete lu;
+        return CFLX_ERR_UNSUPPORTED;
+    }
+    int rc = CFLX_OK;
+    auto fail = [&](int code) {
+        free_lu(lu);
+        return code;
+    };
+    // sub-communicators (all ranks call all splits, same order)
+    if ((rc = make_sub(c, lu->pi * Py + lu->pj, lu->pk, Pz, &lu->k_comm))) return fail(rc);
+    if ((rc = make_sub(c, lu->pj * Pz + lu->pk, lu->pi, Px, &lu->i_comm))) return fail(rc);
+    if ((rc = make_sub(c, lu->pi, lu->pj * Pz + lu->pk, Py * Pz, &lu->jk_comm))) return fail(rc);
+    if ((rc = make_sub(c, lu->pj, lu->pi * Pz + lu->pk, Px * Pz, &lu->ik_comm))) return fail(rc);
+
+    const size_t loc = (size_t)lu->Ml * lu->Nl;
+    const int64_t ldp = round_up(lu->Ml, 2) + 2;
+    lu->ldp_max = ldp;
+    const size_t pan = (size_t)v * ldp, upan = (size_t)v * (lu->Nl + 2), vv = (size_t)v * v;
+#define ALLOC(ptr, n) if ((rc = dmalloc(&(ptr), (n)))) return fail(rc)
+    ALLOC(lu->A0, loc); ALLOC(lu->A11, loc);
+    ALLOC(lu->PT, pan); ALLOC(lu->PT2, pan); ALLOC(lu->W, pan); ALLOC(lu->LT, pan);
+    ALLOC(lu->A01raw, upan); ALLOC(lu->U, upan); ALLOC(lu->tmp, (size_t)v * lu->Nl);
+    ALLOC(lu->A00, vv); ALLOC(lu->A00T, vv); ALLOC(lu->Uinv, vv); ALLOC(lu->LinvT, vv);
+    ALLOC(lu->candH, 2 * vv); ALLOC(lu->S, 2 * vv); ALLOC(lu->W2, 2 * vv); ALLOC(lu->bcast, vv + v);
+    ALLOC(lu->gri, lu->Ml); ALLOC(lu->gri_tmp, lu->Ml); ALLOC(lu->igri, lu->Ml); ALLOC(lu->perm, 2 * v);
+    ALLOC(lu->gpivots, v); ALLOC(lu->tagsH, 2 * v); ALLOC(lu->tagsS, 2 * v); ALLOC(lu->hist, lu->M);
+    ALLOC(lu->plan_mem, 6 * (size_t)v + 8 + lu->Ml);
+#undef ALLOC
+    int* pm = lu->plan_mem;
+    lu->plan.npiv = pm; lu->plan.nel = pm + 4; pm += 8;
+    lu->plan.cur_piv = pm; pm += v;
+    lu->plan.order = pm; pm += v;
+    lu->plan.slot2piv = pm; pm += v;
+    lu->plan.early = pm; pm += v;
+    lu->plan.late = pm; pm += v;
+    pm += v;
+    lu->plan.rowsrc = pm;
+    if (cudaMallocHost((void**)&lu->h_npiv, sizeof(int)) != cudaSuccess) return fail(CFLX_ERR_CUDA);
+    if ((rc = panel_workspace_create(&lu->pws))) return fail(rc);
+    if ((rc = gemm_tn_setup())) return fail(rc);
+    lu->h_hist.assign(lu->M, -1);
+    // zero the panels once: padded columns are read (and masked) by the GEMM producer
+    cudaMemsetAsync(lu->PT, 0, pan * sizeof(double), c->stream);
+    cudaMemsetAsync(lu->PT2, 0, pan * sizeof(double), c->stream);
+    cudaMemsetAsync(lu->LT, 0, pan * sizeof(double), c->stream);
+    cudaMemsetAsync(lu->W, 0, pan * sizeof(double), c->stream);
+    cudaMemsetAsync(lu->A01raw, 0, upan * sizeof(double), c->stream);
+    cudaMemsetAsync(lu->U, 0, upan * sizeof(double), c->stream);
+    cudaMemsetAsync(lu->A0, 0, loc * sizeof(double), c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(CFLX_ERR_CUDA);
+    *out = lu;
+    return CFLX_OK;
+}
+
+int cflx_lu_info(const cflx_lu* lu, int* o) {
+    if (!lu || !o) return CFLX_ERR_ARG;
+    const int vals[16] = {lu->M, lu->N, lu->Ml, lu->Nl, lu->Nt, lu->nlayr, lu->P, lu->Px, lu->Py, lu->Pz, lu->pi, lu->pj,
+                          lu->pk, lu->rank, lu->v, 0};
+    std::memcpy(o, vals, sizeof(vals));
+    return CFLX_OK;
+}
+
+int cflx_lu_set_local(cflx_lu* lu, const double* host_local) {
+    if (!lu || !host_local) return CFLX_ERR_ARG;
+    CFLX_CUDA(cudaSetDevice(lu->comm->device));
+    const size_t loc = (size_t)lu->Ml * lu->Nl;
+    CFLX_CUDA(cudaMemcpyAsync(lu->A0, host_local, loc * sizeof(double), cudaMemcpyHostToDevice, lu->comm->stream));
+    CFLX_CUDA(cudaStreamSynchronize(lu->comm->stream));
+    lu->have_input = true;
+    lu->factored = false;
+    return CFLX_OK;
+}
+
+int cflx_lu_factor(cflx_lu* lu, double* ms_out) {
+    if (!lu) return CFLX_ERR_ARG;
+    if (!lu->have_input) {
+        set_last_error("cflx_lu_factor before cflx_lu_set_local");
+        return CFLX_ERR_STATE;
+    }
+    cflx_comm* c = lu->comm;
+    cudaStream_t s = c->stream;
+    CFLX_CUDA(cudaSetDevice(c->device));
+    const size_t loc = (size_t)lu->Ml * lu->Nl;
+    // "init" region of the reference (conflux_opt.hpp:347-515): A11Buff = copy of gv.data, gri, counters
+    CFLX_CUDA(cudaMemcpyAsync(lu->A11, lu->A0, loc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CFLX_TRY(launch_iota_gri(lu->gri, lu->igri, lu->Ml, lu->v, lu->Px, lu->pi, s));
+    for (double& x : lu->phase_ms) x = 0;
+    CFLX_TRY(grid_barrier(c));  // MPI_Barrier(lu_comm) before t1 (conflux_opt.hpp:531)
+    cudaEvent_t e0, e1;
+    CFLX_CUDA(cudaEventCreate(&e0));
+    CFLX_CUDA(cudaEventCreate(&e1));
+    CFLX_CUDA(cudaEventRecord(e0, s));
+    int fnpr = 0;
+    for (int k = 0; k < lu->Nt; ++k) {
+        int rc = lu_step(lu, k, fnpr);
+        if (rc != CFLX_OK) {
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            return rc;
+        }
+    }
+    CFLX_CUDA(cudaEventRecord(e1, s));
+    CFLX_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    CFLX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CFLX_CUDA(cudaGetLastError());
+    if (ms_out) *ms_out = ms;
+    lu->factored = true;
+    return CFLX_OK;
+}
+
+int cflx_lu_get_permutation(cflx_lu* lu, int* perm_out) {
+    if (!lu || !perm_out) return CFLX_ERR_ARG;
+    if (!lu->factored) {
+        set_last_error("permutation requested before cflx_lu_factor");
+        return CFLX_ERR_STATE;
+    }
+    CFLX_CUDA(cudaSetDevice(lu->comm->device));
+    CFLX_CUDA(cudaMemcpyAsync(lu->h_hist.data(), lu->hist, sizeof(int) * lu->M, cudaMemcpyDeviceToHost, lu->comm->stream));
+    CFLX_CUDA(cudaStreamSynchronize(lu->comm->stream));
+    std::memcpy(perm_out, lu->h_hist.data(), sizeof(int) * lu->M);
+    return CFLX_OK;
+}
+
+// Rows of the finished factors live where their original row lives (local rows are in the order they were
+// promoted).  The reference's validation layout wants pivoted row q = k*v + i on rank (k % Px, pj, 0) at local
+// row (k / Px)*v + i (conflux_opt.hpp:1673-1699,1721-1754): an all-to-all of whole rows inside each grid column.
+int cflx_lu_get_factors(cflx_lu* lu, double* C_host, int* perm_out) {
+    if (!lu) return CFLX_ERR_ARG;
+    if (!lu->factored) {
+        set_last_error("factors requested before cflx_lu_factor");
+        return CFLX_ERR_STATE;
+    }
+    cflx_comm* c = lu->comm;
+    cudaStream_t s = c->stream;
+    CFLX_CUDA(cudaSetDevice(c->device));
+    std::vector<int> hist(lu->M);
+    CFLX_TRY(cflx_lu_get_permutation(lu, hist.data()));
+    if (perm_out) std::memcpy(perm_out, hist.data(), sizeof(int) * lu->M);
+    if (lu->pk != 0) return CFLX_OK;  // only layer 0 holds factors
+    const int v = lu->v, Px = lu->Px, Ml = lu->Ml, Nl = lu->Nl;
+    const size_t loc = (size_t)Ml * Nl;
+    if (!lu->Cbuf) CFLX_TRY(dmalloc(&lu->Cbuf, loc));
+    if (!lu->xbuf) CFLX_TRY(dmalloc(&lu->xbuf, 2 * loc));
+    if (!lu->idx_buf) CFLX_TRY(dmalloc(&lu->idx_buf, 2 * (size_t)Ml));
+    // per source rank: its local row counter; per (src, dst): ordered lists
+    std::vector<int> next_local(Px, 0);
+    std::vector<std::vector<int>> send_rows(Px), recv_rows(Px);  // send_rows[dst] = my local rows; recv_rows[src] = my dest rows
+    for (int q = 0; q < lu->M; ++q) {
+        const int g = hist[q];
+        const int owner = (g / v) % Px;
+        const int lrow = next_local[owner]++;
+        const int k = q / v, i = q % v;
+        const int dst = k % Px, drow = (k / Px) * v + i;
+        if (owner == lu->pi) send_rows[dst].push_back(lrow);
+        if (dst == lu->pi) recv_rows[owner].push_back(drow);
+    }
+    std::vector<int> flat_send, flat_recv;
+    for (int p = 0; p < Px; ++p) flat_send.insert(flat_send.end(), send_rows[p].begin(), send_rows[p].end());
+    for (int p = 0; p < Px; ++p) flat_recv.insert(flat_recv.end(), recv_rows[p].begin(), recv_rows[p].end());
+    if ((int)flat_send.size() != Ml || (int)flat_recv.size() != Ml) {
+        set_last_error("factor redistribution: %zu rows to send, %zu to receive, expected %d", flat_send.size(),
+                       flat_recv.size(), Ml);
+        return CFLX_ERR_STATE;
+    }
+    CFLX_CUDA(cudaMemcpyAsync(lu->idx_buf, flat_send.data(), sizeof(int) * Ml, cudaMemcpyHostToDevice, s));
+    CFLX_CUDA(cudaMemcpyAsync(lu->idx_buf + Ml, flat_recv.data(), sizeof(int) * Ml, cudaMemcpyHostToDevice, s));
+    dim3 grid(std::max(1, std::min(32, Nl / 256)), Ml);
+    double* sendbuf = lu->xbuf;
+    double* recvbuf = lu->xbuf + loc;
+    gather_rows_kernel<<<grid, 256, 0, s>>>(lu->A11, Nl, lu->idx_buf, Ml, Nl, sendbuf);
+    CFLX_CUDA(cudaGetLastError());
+    if (Px > 1) {
+        CFLX_NCCL(ncclGroupStart());
+        size_t so = 0, ro = 0;
+        for (int p = 0; p < Px; ++p) {
+            const size_t ns = send_rows[p].size() * (size_t)Nl, nr = recv_rows[p].size() * (size_t)Nl;
+            if (p == lu->pi) {
+                CFLX_CUDA(cudaMemcpyAsync(recvbuf + ro, sendbuf + so, ns * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            } else {
+                if (ns) CFLX_NCCL(ncclSend(sendbuf + so, ns, ncclDouble, p, lu->i_comm.c, s));
+                if (nr) CFLX_NCCL(ncclRecv(recvbuf + ro, nr, ncclDouble, p, lu->i_comm.c, s));
+            }
+            so += ns;
+            ro += nr;
+        }
+        CFLX_NCCL(ncclGroupEnd());
+    } else {
+        recvbuf = sendbuf;
+    }
+    scatter_rows_kernel<<<grid, 256, 0, s>>>(recvbuf, Nl, lu->idx_buf + Ml, Ml, lu->Cbuf, Nl);
+    CFLX_CUDA(cudaGetLastError());
+    if (C_host) CFLX_CUDA(cudaMemcpyAsync(C_host, lu->Cbuf, loc * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CFLX_CUDA(cudaStreamSynchronize(s));
+    return CFLX_OK;
+}
+
+int cflx_lu_launch_count(cflx_lu* lu, int64_t* count_out, int reset) {
+    if (!lu || !count_out) return CFLX_ERR_ARG;
+    *count_out = lu->launches;
+    if (reset) lu->launches = 0;
+    return CFLX_OK;
+}
+int cflx_lu_set_profiling(cflx_lu* lu, int enabled) {
+    if (!lu) return CFLX_ERR_ARG;
+    lu->profiling = enabled != 0;
+    return CFLX_OK;
+}
+int cflx_lu_phase_ms(cflx_lu* lu, double* ms_out) {
+    if (!lu || !ms_out) return CFLX_ERR_ARG;
+    for (int i = 0; i < PH_COUNT; ++i) ms_out[i] = lu->phase_ms[i];
+    return CFLX_OK;
+}
+void cflx_lu_destroy(cflx_lu* lu) { free_lu(lu); }
+
+}  // extern "C"

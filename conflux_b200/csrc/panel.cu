@@ -1,0 +1,377 @@
+// conflux_b200/csrc/panel.cu -- tournament-pivot panel factorisation kernel (K1 of SURVEY.md 2.3).
+//
+// Replaces LUP = LAPACKE_dgetrf(ROW_MAJOR, n, v) + ipiv->perm at
+// /root/reference/src/conflux/lu/conflux_opt.hpp:143-166 (called at :727 for the local candidates and at :291 for
+// every 2v x v tournament round).  Only two things of that factorisation are kept by the reference: the winners
+// perm[0..v) and (last round) the top v x v block L00\U00; this kernel produces exactly those.
+//
+// Design (B200-first, not a LAPACK translation):
+//   * the panel is stored TRANSPOSED, W[c][r]: a pivot search over column c is a coalesced scan of one row of W;
+//   * one persistent cooperative grid (<= 148 CTAs, one per SM); thread <-> matrix row; rows NEVER move: LAPACK's
+//     interchanges are tracked as a per-row "position" so that idamax tie-breaking (first maximal |a| in the
+//     swapped order) is reproduced exactly (needed for the reference's integer test matrices);
+//   * right-looking with an NB-column inner block held in shared memory; per column ONE grid-wide exchange:
+//     every CTA publishes its best candidate together with that row's inner-block values into a double-buffered
+//     global slot (st.release.gpu), then reads all slots (ld.acquire.gpu) and picks the winner redundantly --
+//     no second round trip for the pivot row, no grid barrier;
+//   * warp-level argmax with redux.sync on the (hi, lo) words of |a| and the position;
+//   * after NB columns each CTA redundantly solves U12 = L11^-1 A12 (NB x rem, shared memory) and applies the
+//     rank-NB update to its own rows with the multipliers in registers; CTA 0 emits the rows of L00\U00.
+#include <cooperative_groups.h>
+
+#include <climits>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cflx {
+
+namespace {
+constexpr int PT_THREADS = 128;
+constexpr int PT_WARPS = PT_THREADS / 32;
+constexpr int MAXG = 148;
+constexpr int RPT_MAX = 4;  // rows per thread -> R <= 512 rows per CTA
+
+struct PanelArgs {
+    double* W;
+    int64_t ldw;
+    int n, v, nsteps;
+    int R, Rpad, G;
+    int* perm_out;
+    double* A00;  // may be null: rows of L00\U00 from the pivot's inner block on
+    double* slot_rows;
+    double* slot_val;
+    int* slot_pos;
+    int* slot_row;
+    int* slot_flag;
+    int epoch_base;
+};
+
+struct Cand {
+    unsigned long long key;  // bits of |a| (monotone for non-negative doubles)
+    int pos;                 // LAPACK position (tie-break: smaller wins); INT_MAX = no candidate
+    int row;
+};
+
+__device__ __forceinline__ Cand warp_argmax(Cand c) {
+    const unsigned hi = (unsigned)(c.key >> 32), lo = (unsigned)c.key;
+    const unsigned m1 = __reduce_max_sync(0xffffffffu, hi);
+    bool in = (hi == m1);
+    const unsigned m2 = __reduce_max_sync(0xffffffffu, in ? lo : 0u);
+    in = in && (lo == m2);
+    const unsigned m3 = __reduce_min_sync(0xffffffffu, in ? (unsigned)c.pos : (unsigned)INT_MAX);
+    const unsigned ballot = __ballot_sync(0xffffffffu, in && (unsigned)c.pos == m3);
+    const int src = __ffs(ballot) - 1;
+    Cand r;
+    r.key = ((unsigned long long)m1 << 32) | m2;
+    r.pos = (int)m3;
+    r.row = __shfl_sync(0xffffffffu, c.row, src);
+    return r;
+}
+__device__ __forceinline__ bool better(const Cand& a, const Cand& b) {  // a strictly better than b
+    return a.key > b.key || (a.key == b.key && a.pos < b.pos);
+}
+// block-wide argmax; result identical in every thread.  red_* have PT_WARPS entries.
+__device__ __forceinline__ Cand block_argmax(Cand c, unsigned long long* red_key, int* red_pos, int* red_row) {
+    Cand w = warp_argmax(c);
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        red_key[warp] = w.key;
+        red_pos[warp] = w.pos;
+        red_row[warp] = w.row;
+    }
+    __syncthreads();
+    Cand best{red_key[0], red_pos[0], red_row[0]};
+#pragma unroll
+    for (int i = 1; i < PT_WARPS; ++i) {
+        Cand o{red_key[i], red_pos[i], red_row[i]};
+        if (better(o, best)) best = o;
+    }
+    __syncthreads();  // red_* may be reused right away
+    return best;
+}
+
+template <int NB>
+__global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* Ab = reinterpret_cast<double*>(smem_raw);  // [NB][Rpad] inner block, column-major per CTA
+    double* U12 = Ab + (size_t)NB * p.Rpad;            // [NB][v]
+    double* LU11 = U12 + (size_t)NB * p.v;             // [NB][NB+1] LU rows of this block's pivots
+    double* prow = LU11 + NB * (NB + 1);               // [NB]
+    unsigned long long* red_key = reinterpret_cast<unsigned long long*>(prow + NB);
+    int* red_pos = reinterpret_cast<int*>(red_key + PT_WARPS);
+    int* red_row = red_pos + PT_WARPS;
+    int* pivrow_blk = red_row + PT_WARPS;  // [NB]
+
+    const int t = threadIdx.x;
+    const int cta = blockIdx.x;
+    const int row_base = cta * p.R;
+    const int Rloc = max(0, min(p.R, p.n - row_base));
+    const int Rpad = p.Rpad, v = p.v;
+    double* __restrict__ W = p.W;
+    const int64_t ldw = p.ldw;
+
+    int pos[RPT_MAX];
+    bool active[RPT_MAX];
+    int pib[RPT_MAX];  // pivot index inside the current block, -1 otherwise
+#pragma unroll
+    for (int q = 0; q < RPT_MAX; ++q) {
+        const int lr = t + q * PT_THREADS;
+        pos[q] = row_base + lr;
+        active[q] = lr < Rloc;
+        pib[q] = -1;
+    }
+
+    for (int jb = 0; jb < p.nsteps; jb += NB) {
+        const int nbc = min(NB, v - jb);         // columns in this block
+        const int nsb = min(nbc, p.nsteps - jb);  // elimination steps in this block
+        // ---- phase A: load the inner block of my rows (coalesced rows of W) ----
+        for (int c = 0; c < nbc; ++c) {
+#pragma unroll
+            for (int q = 0; q < RPT_MAX; ++q) {
+                const int lr = t + q * PT_THREADS;
+                if (lr < Rloc) Ab[c * Rpad + lr] = W[(int64_t)(jb + c) * ldw + row_base + lr];
+            }
+        }
+        // (each thread touches only its own rows of Ab until a winner row is published after a block sync)
+
+        // ---- phase B: nsb pivot steps ----
+        for (int j = 0; j < nsb; ++j) {
+            const int jg = jb + j;
+            Cand c{0ull, INT_MAX, -1};
+#pragma unroll
+            for (int q = 0; q < RPT_MAX; ++q) {
+                const int lr = t + q * PT_THREADS;
+                if (active[q]) {
+                    Cand o{(unsigned long long)__double_as_longlong(fabs(Ab[j * Rpad + lr])), pos[q], row_base + lr};
+                    if (better(o, c)) c = o;
+                }
+            }
+            const Cand mine = block_argmax(c, red_key, red_pos, red_row);
+            // publish my CTA's candidate and its inner-block row
+            const int par = jg & 1;
+            const int myslot = par * MAXG + cta;
+            const int epoch = p.epoch_base + jg + 1;
+            if (mine.row >= 0 && t < nbc) p.slot_rows[(size_t)myslot * 32 + t] = Ab[t * Rpad + (mine.row - row_base)];
+            __syncthreads();
+            if (t == 0) {
+                p.slot_val[myslot] = __longlong_as_double((long long)mine.key);
+                p.slot_pos[myslot] = mine.pos;
+                p.slot_row[myslot] = mine.row;
+                __threadfence();
+                st_release_gpu(&p.slot_flag[myslot], epoch);
+            }
+            // gather every CTA's candidate
+            Cand gc{0ull, INT_MAX, -1};
+            for (int g = t; g < p.G; g += PT_THREADS) {
+                const int s = par * MAXG + g;
+                while (ld_acquire_gpu(&p.slot_flag[s]) != epoch) {
+                }
+                Cand o{(unsigned long long)__double_as_longlong(ld_cg_f64(&p.slot_val[s])), ld_cg_s32(&p.slot_pos[s]),
+                       ld_cg_s32(&p.slot_row[s])};
+                if (better(o, gc)) gc = o;
+            }
+            const Cand win = block_argmax(gc, red_key, red_pos, red_row);
+            // (win.row < 0 cannot happen while jg < nsteps = min(n, v): some row is still active)
+            const int wcta = win.row / p.R;
+            if (t < nbc) {
+                const double x = ld_cg_f64(&p.slot_rows[(size_t)(par * MAXG + wcta) * 32 + t]);
+                prow[t] = x;
+                LU11[j * (NB + 1) + t] = x;
+            }
+            if (t == 0) {
+                pivrow_blk[j] = win.row;
+                if (cta == 0) p.perm_out[jg] = win.row;
+            }
+            __syncthreads();
+            const double pivot = prow[j];
+            const double rinv = pivot != 0.0 ? 1.0 / pivot : 0.0;
+#pragma unroll
+            for (int q = 0; q < RPT_MAX; ++q) {
+                const int lr = t + q * PT_THREADS;
+                if (!active[q]) continue;
+                if (row_base + lr == win.row) {
+                    active[q] = false;
+                    pib[q] = j;
+                    continue;
+                }
+                if (pos[q] == jg) pos[q] = win.pos;  // the row that sat at position jg moves to the winner's slot
+                if (pivot != 0.0) {
+                    const double l = Ab[j * Rpad + lr] * rinv;
+                    Ab[j * Rpad + lr] = l;
+                    for (int c2 = j + 1; c2 < nbc; ++c2) Ab[c2 * Rpad + lr] -= l * prow[c2];
+                }
+            }
+            // next step's block_argmax syncs before prow / LU11 are overwritten
+        }
+
+        // ---- write the inner block back (L multipliers; pivot rows keep their LU row) ----
+        for (int c = 0; c < nbc; ++c) {
+#pragma unroll
+            for (int q = 0; q < RPT_MAX; ++q) {
+                const int lr = t + q * PT_THREADS;
+                if (lr < Rloc) W[(int64_t)(jb + c) * ldw + row_base + lr] = Ab[c * Rpad + lr];
+            }
+        }
+        if (cta == 0 && p.A00 != nullptr) {
+            for (int e = t; e < nsb * nbc; e += PT_THREADS) {
+                const int i = e / nbc, c = e % nbc;
+                p.A00[(size_t)(jb + i) * v + jb + c] = LU11[i * (NB + 1) + c];
+            }
+        }
+
+        // ---- phase C: U12 = L11^-1 A12, trailing columns of my rows -= L21 * U12 ----
+        const int cstart = jb + nbc;
+        const int rem = v - cstart;
+        if (rem > 0) {
+            __syncthreads();  // pivrow_blk, LU11 complete
+            for (int e = t; e < nsb * rem; e += PT_THREADS) {
+                const int i = e / rem, cc = e % rem;
+                U12[i * v + cc] = ld_cg_f64(&W[(int64_t)(cstart + cc) * ldw + pivrow_blk[i]]);
+            }
+            __syncthreads();
+            for (int cc = t; cc < rem; cc += PT_THREADS) {  // unit-lower forward substitution, one column per thread
+                for (int i = 1; i < nsb; ++i) {
+                    double u = U12[i * v + cc];
+                    for (int s2 = 0; s2 < i; ++s2) u -= LU11[i * (NB + 1) + s2] * U12[s2 * v + cc];
+                    U12[i * v + cc] = u;
+                }
+            }
+            __syncthreads();
+            if (cta == 0 && p.A00 != nullptr) {
+                for (int e = t; e < nsb * rem; e += PT_THREADS) {
+                    const int i = e / rem, cc = e % rem;
+                    p.A00[(size_t)(jb + i) * v + cstart + cc] = U12[i * v + cc];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < RPT_MAX; ++q) {
+                const int lr = t + q * PT_THREADS;
+                if (lr >= Rloc || !active[q]) continue;  // finished pivot rows are never read again
+                double l[NB];
+#pragma unroll
+                for (int i = 0; i < NB; ++i) l[i] = (i < nsb) ? Ab[i * Rpad + lr] : 0.0;
+                double* wp = W + (int64_t)cstart * ldw + row_base + lr;
+                int cc = 0;
+                for (; cc + 1 < rem; cc += 2) {
+                    double w0 = wp[(int64_t)cc * ldw], w1 = wp[(int64_t)(cc + 1) * ldw];
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) {
+                        w0 -= l[i] * U12[i * v + cc];
+                        w1 -= l[i] * U12[i * v + cc + 1];
+                    }
+                    wp[(int64_t)cc * ldw] = w0;
+                    wp[(int64_t)(cc + 1) * ldw] = w1;
+                }
+                if (cc < rem) {
+                    double w0 = wp[(int64_t)cc * ldw];
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) w0 -= l[i] * U12[i * v + cc];
+                    wp[(int64_t)cc * ldw] = w0;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < RPT_MAX; ++q) pib[q] = -1;
+        __syncthreads();  // Ab / U12 / LU11 are rewritten by the next block
+    }
+    // identity tail of perm (n < v): LAPACK leaves perm[i] = i for i >= n (conflux_opt.hpp:150-165)
+    if (cta == 0)
+        for (int i = p.nsteps + t; i < v; i += PT_THREADS) p.perm_out[i] = i;
+}
+
+template <int NB>
+size_t panel_smem_bytes(int Rpad, int v) {
+    return ((size_t)NB * Rpad + (size_t)NB * v + NB * (NB + 1) + NB) * sizeof(double) +
+           PT_WARPS * (sizeof(unsigned long long) + 2 * sizeof(int)) + NB * sizeof(int) + 64;
+}
+
+template <int NB>
+int launch_nb(PanelArgs& a, cudaStream_t stream) {
+    const size_t smem = panel_smem_bytes<NB>(a.Rpad, a.v);
+    static size_t configured = 0;
+    if (smem > configured) {
+        CFLX_CUDA(cudaFuncSetAttribute(panel_getrf_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    void* params[] = {&a};
+    CFLX_CUDA(cudaLaunchCooperativeKernel((void*)panel_getrf_kernel<NB>, dim3(a.G), dim3(PT_THREADS), params, smem,
+                                          stream));
+    return CFLX_OK;
+}
+}  // namespace
+
+int panel_workspace_create(PanelWorkspace* ws) {
+    int dev = 0, sms = 0;
+    CFLX_CUDA(cudaGetDevice(&dev));
+    CFLX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    ws->max_ctas = sms < MAXG ? sms : MAXG;
+    ws->epoch = 0;
+    CFLX_CUDA(cudaMalloc(&ws->slot_rows, sizeof(double) * 2 * MAXG * 32));
+    CFLX_CUDA(cudaMalloc(&ws->slot_val, sizeof(double) * 2 * MAXG));
+    CFLX_CUDA(cudaMalloc(&ws->slot_pos, sizeof(int) * 2 * MAXG));
+    CFLX_CUDA(cudaMalloc(&ws->slot_row, sizeof(int) * 2 * MAXG));
+    CFLX_CUDA(cudaMalloc(&ws->slot_flag, sizeof(int) * 2 * MAXG));
+    CFLX_CUDA(cudaMemset(ws->slot_flag, 0, sizeof(int) * 2 * MAXG));
+    return CFLX_OK;
+}
+void panel_workspace_destroy(PanelWorkspace* ws) {
+    cudaFree(ws->slot_rows);
+    cudaFree(ws->slot_val);
+    cudaFree(ws->slot_pos);
+    cudaFree(ws->slot_row);
+    cudaFree(ws->slot_flag);
+    *ws = PanelWorkspace{};
+}
+
+// A00 (optional, v x v row-major) receives, for pivot i, the columns >= (i / NB) * NB of its L\U row; the
+// caller completes the L prefix with launch_gather_a00 (which also needs perm).
+int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, double* A00, int* nb_used,
+                           PanelWorkspace* ws, cudaStream_t stream) {
+    if (v <= 0 || n < 0) return CFLX_ERR_ARG;
+    PanelArgs a{};
+    a.W = W;
+    a.ldw = ldw;
+    a.n = n;
+    a.v = v;
+    a.nsteps = n < v ? n : v;
+    int G = (n + PT_THREADS - 1) / PT_THREADS;
+    if (G < 1) G = 1;
+    if (G > ws->max_ctas) G = ws->max_ctas;
+    int R = (n + G - 1) / G;
+    R = (int)round_up(R > 0 ? R : 1, 32);
+    G = n > 0 ? (n + R - 1) / R : 1;
+    if (R > RPT_MAX * PT_THREADS) {
+        set_last_error("panel_getrf: n=%d rows exceed the %d-row capacity", n, ws->max_ctas * RPT_MAX * PT_THREADS);
+        return CFLX_ERR_UNSUPPORTED;
+    }
+    a.R = R;
+    a.Rpad = R;
+    a.G = G;
+    a.perm_out = perm_out;
+    a.A00 = A00;
+    a.slot_rows = ws->slot_rows;
+    a.slot_val = ws->slot_val;
+    a.slot_pos = ws->slot_pos;
+    a.slot_row = ws->slot_row;
+    a.slot_flag = ws->slot_flag;
+    a.epoch_base = ws->epoch;
+    ws->epoch += v + 2 + (v & 1);  // keep the base even so slot parity == column parity
+    const size_t budget = 200 * 1024;
+    int nb = v >= 32 ? 32 : (v >= 16 ? 16 : (v >= 8 ? 8 : 4));
+    if (nb == 32 && panel_smem_bytes<32>(a.Rpad, v) > budget) nb = 16;
+    if (nb == 16 && panel_smem_bytes<16>(a.Rpad, v) > budget) nb = 8;
+    if (nb_used) *nb_used = nb;
+    switch (nb) {
+        case 32: return launch_nb<32>(a, stream);
+        case 16: return launch_nb<16>(a, stream);
+        case 8: return launch_nb<8>(a, stream);
+        default: return launch_nb<4>(a, stream);
+    }
+}
+
+int launch_panel_getrf(double* W, int64_t ldw, int n, int v, int* perm_out, PanelWorkspace* ws, cudaStream_t stream) {
+    return launch_panel_getrf_a00(W, ldw, n, v, perm_out, nullptr, nullptr, ws, stream);
+}
+
+}  // namespace cflx

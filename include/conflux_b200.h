@@ -1,0 +1,103 @@
+/*
+ * include/conflux_b200.h -- C ABI of the B200-native CONFLUX LU hot path (libconflux_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of eth-cscs/conflux: conflux::LU_rep<double> and the parts of
+ * conflux::lu_params<double> it needs.  Plain pointers and sizes only; every function returns 0 on success or
+ * a negative status code (never throws, never aborts); cflx_last_error() gives the message of the last failure
+ * on the calling thread.  SPMD like the reference: one host thread (or process) per rank = per GPU; every
+ * entry point that is marked COLLECTIVE must be called by all ranks of the grid in the same order.
+ *
+ * Reference interfaces replaced (file:line relative to the reference repository):
+ *   MPI_Comm / MPI_Init / MPI_Cart_create ............ src/conflux/lu/lu_params.hpp:85-108   -> cflx_comm_*
+ *   lu_params<T>::initialize (sizes, grid, comms) .... src/conflux/lu/lu_params.hpp:49-138   -> cflx_lu_create
+ *   lu_params<T>::get_p_grid ......................... src/conflux/lu/lu_params.hpp:21-47    -> cflx_auto_grid
+ *   lu_params<T>::InitMatrix (seeded generator) ...... src/conflux/lu/lu_params.hpp:364-375  -> cflx_init_matrix_host
+ *   lu_params<T>::data (local tiles, ld = Nl) ........ src/conflux/lu/layout.cpp:95-109      -> cflx_lu_set_local
+ *   LU_rep<T>(gv, C, permutation) main loop .......... src/conflux/lu/conflux_opt.hpp:343-1827 -> cflx_lu_factor
+ *   validation outputs C / permutation ............... src/conflux/lu/conflux_opt.hpp:1660-1771,1822 -> cflx_lu_get_factors
+ * There is no CPU fallback: without a CUDA device every device entry point returns CFLX_ERR_NO_DEVICE.
+ */
+#ifndef CONFLUX_B200_H
+#define CONFLUX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    CFLX_OK = 0,
+    CFLX_ERR_ARG = -1,         /* invalid argument */
+    CFLX_ERR_CUDA = -2,        /* CUDA runtime failure */
+    CFLX_ERR_NCCL = -3,        /* NCCL failure */
+    CFLX_ERR_UNSUPPORTED = -4, /* shape/grid outside the supported envelope (Px != Py, v % 4, ...) */
+    CFLX_ERR_STATE = -5,       /* call order violated (e.g. get_factors before factor) */
+    CFLX_ERR_NO_DEVICE = -6    /* no CUDA device visible: the library refuses to run (no CPU fallback) */
+} cflx_status;
+
+typedef struct cflx_comm cflx_comm; /* process grid handle: one per rank, owns the NCCL communicators */
+typedef struct cflx_lu cflx_lu;     /* one factorisation plan: sizes, device buffers, pivot history */
+
+#define CFLX_UNIQUE_ID_BYTES 128
+
+const char* cflx_last_error(void);
+const char* cflx_version(void);
+int cflx_device_count(int* count);
+
+/* ---- process grid (replaces MPI_COMM_WORLD + MPI_Cart_create/sub) ------------------------------------ */
+/* rank 0 creates an id and ships it to the other ranks by any host channel (MPI, torch.distributed, a file) */
+int cflx_get_unique_id(void* id_out /* CFLX_UNIQUE_ID_BYTES */);
+/* COLLECTIVE.  world_size == 1 needs no id (may be NULL).  device = CUDA ordinal this rank drives. */
+int cflx_comm_create(int world_size, int world_rank, const void* unique_id, int device, cflx_comm** out);
+int cflx_comm_barrier(cflx_comm*); /* COLLECTIVE: device-side barrier + host synchronisation */
+void cflx_comm_destroy(cflx_comm*);
+
+/* ---- sizes (pure host arithmetic, no device needed) ---------------------------------------------------- */
+/* lu_params::get_p_grid for a square matrix: P = 1 -> 1x1x1, 2 -> 1x1x2, 4 -> 2x2x1, 8 -> 2x2x2, ... */
+int cflx_auto_grid(int M, int N, int P, int* Px, int* Py, int* Pz);
+/* dims_out[8] = {M, N, Ml, Nl, Nt, nlayr, Mt, P} after padding, exactly as lu_params::initialize */
+int cflx_lu_dims(int M, int N, int v, int Px, int Py, int Pz, int* dims_out);
+/* lu_params::InitMatrix, random branch: fills the Ml x Nl row-major local array of `rank` (layers pk != 0 zero) */
+int cflx_init_matrix_host(int M, int N, int v, int Px, int Py, int Pz, int rank, int seed, double* local_out);
+
+/* ---- the factorisation ----------------------------------------------------------------------------------- */
+/* COLLECTIVE.  Px <= 0 selects cflx_auto_grid(world_size).  Requires Px == Py, Px*Py*Pz == world_size,
+ * v % 4 == 0, (v / Pz) % 4 == 0.  Allocates all device memory of the plan. */
+int cflx_lu_create(cflx_comm*, int M, int N, int v, int Px, int Py, int Pz, cflx_lu** out);
+/* info_out[16] = {M, N, Ml, Nl, Nt, nlayr, P, Px, Py, Pz, pi, pj, pk, rank, v, 0} */
+int cflx_lu_info(const cflx_lu*, int* info_out);
+/* host -> device copy of this rank's local matrix (conflux tile layout, row-major, ld = Nl); kept pristine */
+int cflx_lu_set_local(cflx_lu*, const double* host_local);
+/* COLLECTIVE.  Runs steps 0..Nt-1 on the GPU(s).  ms_out = device time of the main loop only (CUDA events on
+ * this rank's stream, after a grid barrier) -- the region the reference times (conflux_opt.hpp:531-532,1805). */
+int cflx_lu_factor(cflx_lu*, double* ms_out);
+/* COLLECTIVE.  C_host (Ml x Nl, may be NULL on layers pk != 0): L\U of P*A in the conflux layout, row
+ * (k/Px)*v + i of rank (k%Px, pj, 0) = pivoted row k*v + i; permutation_out[M] = pivotIndsBuff. */
+int cflx_lu_get_factors(cflx_lu*, double* C_host, int* permutation_out);
+/* device -> host copy of the permutation only (the cheap "result" of a run) */
+int cflx_lu_get_permutation(cflx_lu*, int* permutation_out);
+/* number of kernels this plan launched since the last call (for bench.py's gpu_launches) */
+int cflx_lu_launch_count(cflx_lu*, int64_t* count_out, int reset);
+/* per-phase device time of the last cflx_lu_factor when profiling was enabled: ms_out[8] =
+ * {panel, tournament+bcast, row moves, reduce+gather, trsm, gemm, stores, other} */
+int cflx_lu_set_profiling(cflx_lu*, int enabled);
+int cflx_lu_phase_ms(cflx_lu*, double* ms_out);
+void cflx_lu_destroy(cflx_lu*);
+
+/* ---- single-device building blocks exposed for tests and micro-benchmarks (host buffers in, host out) ----- */
+/* D = beta*C + alpha * AT^T * B with AT [K x M], B [K x N], C/D [M x N], all row-major, dense */
+int cflx_dbg_gemm_tn(int M, int N, int K, const double* AT, const double* B, const double* C, double alpha, double beta,
+                     double* D, int reps, double* ms_out);
+/* partial-pivot LU of an n x v row-major panel: perm_out[v], A00_out[v*v] (L00\U00), LU_out[n*v] rows unpermuted */
+int cflx_dbg_panel(int n, int v, const double* panel, int* perm_out, double* A00_out, double* LU_out, int reps,
+                   double* ms_out);
+/* X = B * U^-1 (right, upper, non-unit; B n x v) and Y = L^-1 * R (left, lower, unit; R v x n), A00 = L\U packed */
+int cflx_dbg_trsm(int n, int v, const double* A00, const double* B, double* X_out, const double* R, double* Y_out);
+/* raw FP64 pipe micro-benchmarks: which = 0 DMMA (mma.sync m8n8k4 f64), 1 DFMA; returns TFLOP/s */
+int cflx_dbg_fp64_peak(int which, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONFLUX_B200_H */

@@ -1,0 +1,57 @@
+"""CPU: the C-ABI library loads and exports every symbol include/conflux_b200.h declares; host-only entry points
+work; device entry points refuse loudly without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import conflux_b200 as cb
+from conflux_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "conflux_b200.h")).read()
+    declared = set(re.findall(r"\b(cflx_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for s in declared:
+        assert hasattr(L, s), s
+
+
+def test_auto_grid_matches_reference_rule():
+    # lu_params.hpp:21-47: 1 -> 1x1x1, 2 -> 1x1x2, 4 -> 2x2x1, 8 -> 2x2x2, 9 -> 3x3x1, 16 -> 4x4x1, 18 -> 3x3x2
+    for P, g in [(1, (1, 1, 1)), (2, (1, 1, 2)), (4, (2, 2, 1)), (8, (2, 2, 2)), (9, (3, 3, 1)), (16, (4, 4, 1)),
+                 (18, (3, 3, 2))]:
+        assert cb.auto_grid(4096, 4096, P) == g
+
+
+def test_dims_match_reference_rule():
+    d = cb.lu_dims(65536, 65536, 512, 2, 2, 2)
+    assert (d["M"], d["Ml"], d["Nl"], d["Nt"], d["nlayr"]) == (65536, 32768, 32768, 128, 256)
+    d = cb.lu_dims(1000, 1000, 256, 1, 1, 1)       # padding to a multiple of v*Px (lu_params.hpp:67-71)
+    assert (d["M"], d["N"], d["Nt"]) == (1024, 1024, 4)
+    d = cb.lu_dims(27, 27, 3, 3, 3, 1)
+    assert (d["Ml"], d["Nl"], d["Nt"]) == (9, 9, 9)
+
+
+def test_init_matrix_host_is_the_reference_generator():
+    from oracle import restate
+    for (N, v, g) in [(64, 8, (2, 2, 2)), (96, 16, (1, 1, 1)), (72, 4, (3, 3, 2))]:
+        ref = restate.init_matrix(N, v, *g)
+        for rank in range(g[0] * g[1] * g[2]):
+            assert np.array_equal(cb.init_matrix_host(N, N, v, *g, rank), ref[rank])
+
+
+def test_device_entry_points_refuse_without_gpu():
+    n = ctypes.c_int(-1)
+    assert _lib.lib().cflx_device_count(ctypes.byref(n)) == 0
+    if n.value > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(cb.ConfluxError, match="no CPU fallback"):
+        cb.Comm(1, 0, None, 0)
+    with pytest.raises(cb.ConfluxError, match="no CPU fallback"):
+        cb.dbg.gemm_tn(np.ones((4, 4)), np.ones((4, 4)))

@@ -1,0 +1,95 @@
+"""GPU: the whole LU hot path through the reference-facing interface (lu_params / LU_rep) against the oracle, the
+golden fixtures produced by the reference itself, and size-independent properties at larger N."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import layout, restate
+from tests._harness import gpu_lu, n_gpus
+
+pytestmark = pytest.mark.gpu
+RESIDUAL_TOL = 1e-12      # BASELINE.json: ||PA - LU||_F / ||A||_F <= 1e-12
+FACTOR_TOL = 1e-10        # L\U element-wise vs the restatement, relative to ||A||_max
+
+
+def _check_against_oracle(N, v, Px, Py, Pz, A_locals=None):
+    if n_gpus() < Px * Py * Pz:
+        pytest.skip(f"needs {Px * Py * Pz} GPUs")
+    g = gpu_lu(N, v, Px, Py, Pz, A_locals=A_locals)
+    o = restate.lu(g["A"], N, v, Px, Py, Pz)
+    for p in g["perms"]:
+        assert np.array_equal(p, g["perm"])                       # every rank holds the same permutation
+    assert sorted(g["perm"]) == list(range(g["dims"]["M"]))      # it is a permutation
+    assert np.array_equal(g["perm"], o["perm"]), (N, v, Px, Py, Pz)
+    scale = max(np.abs(a).max() for a in g["A"])
+    for r in range(len(g["C"])):
+        if r % Pz == 0:
+            assert np.abs(g["C"][r] - o["C"][r]).max() <= FACTOR_TOL * scale, r
+    A = layout.assemble(g["A"], N, v, Px, Py, Pz)
+    LU = layout.assemble(g["C"], N, v, Px, Py, Pz)
+    assert layout.residual(A, LU, g["perm"]) <= RESIDUAL_TOL
+    return g
+
+
+@pytest.mark.parametrize("N,v", [(16, 4), (64, 8), (96, 16), (256, 32), (512, 64), (1024, 128), (768, 256)])
+def test_single_gpu_matches_oracle(N, v):
+    _check_against_oracle(N, v, 1, 1, 1)
+
+
+def test_single_gpu_padding_of_non_multiple_sizes():
+    g = _check_against_oracle(100, 16, 1, 1, 1)                   # padded to 112 (lu_params.hpp:67-71)
+    assert g["dims"]["M"] == 112
+
+
+def test_single_gpu_golden_fixtures(golden_dir):
+    G = np.load(os.path.join(golden_dir, "lu_cases.npz"))
+    for i, (N, v, Px, Py, Pz) in enumerate(G["cases"]):
+        if (Px, Py, Pz) != (1, 1, 1) or v % 4:
+            continue
+        g = gpu_lu(int(N), int(v), A_locals=list(G[f"c{i}_A"]))
+        assert np.array_equal(g["perm"], G[f"c{i}_perm"])
+        assert np.abs(g["C"][0].reshape(-1) - G[f"c{i}_C"][0]).max() <= FACTOR_TOL * np.abs(G[f"c{i}_A"]).max()
+    Pm = np.load(os.path.join(golden_dir, "lu_perms.npz"))
+    for i, (N, v, Px, Py, Pz) in enumerate(Pm["cases"]):
+        if (Px, Py, Pz) == (1, 1, 1):
+            g = gpu_lu(int(N), int(v), want_C=False)
+            assert np.array_equal(g["perm"], Pm[f"p{i}"]), (N, v)
+
+
+def test_single_gpu_larger_residual_property():
+    N, v = 4096, 256
+    g = gpu_lu(N, v)
+    A, LU = g["A"][0], g["C"][0]
+    assert sorted(g["perm"]) == list(range(N))
+    assert layout.residual(A, LU, g["perm"]) <= RESIDUAL_TOL
+    assert np.abs(np.tril(LU, -1)).max() <= 1.0 + 1e-12          # partial pivoting inside each panel: |l| <= 1
+
+
+def test_repeat_is_deterministic_and_input_untouched():
+    a = gpu_lu(512, 64)
+    b = gpu_lu(512, 64)
+    assert np.array_equal(a["perm"], b["perm"]) and np.array_equal(a["C"][0], b["C"][0])
+
+
+GRIDS = [(64, 8, 2, 2, 1), (128, 16, 1, 1, 2), (128, 8, 2, 2, 2), (512, 32, 2, 2, 1), (512, 64, 2, 2, 2),
+         (1024, 128, 1, 1, 2)]
+
+
+@pytest.mark.parametrize("N,v,Px,Py,Pz", GRIDS)
+def test_multi_gpu_matches_oracle(N, v, Px, Py, Pz):
+    _check_against_oracle(N, v, Px, Py, Pz)
+
+
+def test_multi_gpu_golden_fixtures(golden_dir):
+    G = np.load(os.path.join(golden_dir, "lu_cases.npz"))
+    ran = 0
+    for i, (N, v, Px, Py, Pz) in enumerate(G["cases"]):
+        P = int(Px * Py * Pz)
+        if P == 1 or v % 4 or (v // Pz) % 4 or n_gpus() < P:
+            continue
+        g = gpu_lu(int(N), int(v), int(Px), int(Py), int(Pz), A_locals=list(G[f"c{i}_A"]))
+        assert np.array_equal(g["perm"], G[f"c{i}_perm"])
+        ran += 1
+    if ran == 0:
+        pytest.skip("needs more GPUs")
