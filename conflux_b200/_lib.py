@@ -23,7 +23,7 @@ SYMBOLS = [
     "cflx_comm_barrier", "cflx_comm_destroy", "cflx_auto_grid", "cflx_lu_dims", "cflx_init_matrix_host",
     "cflx_lu_create", "cflx_lu_info", "cflx_lu_set_local", "cflx_lu_factor", "cflx_lu_get_factors",
     "cflx_lu_get_permutation", "cflx_lu_launch_count", "cflx_lu_set_profiling", "cflx_lu_phase_ms",
-    "cflx_lu_destroy", "cflx_dbg_gemm_tn", "cflx_dbg_panel", "cflx_dbg_trsm", "cflx_dbg_fp64_peak",
+    "cflx_lu_set_kernel_timing", "cflx_lu_trailing_stats", "cflx_lu_destroy", "cflx_dbg_gemm_tn", "cflx_dbg_panel", "cflx_dbg_trsm", "cflx_dbg_fp64_peak",
 ]
 
 
@@ -53,6 +53,8 @@ def lib():
         L.cflx_lu_launch_count.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]
         L.cflx_lu_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.cflx_lu_phase_ms.argtypes = [ctypes.c_void_p, c_double_p]
+        L.cflx_lu_set_kernel_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.cflx_lu_trailing_stats.argtypes = [ctypes.c_void_p, c_double_p, c_double_p]
         L.cflx_init_matrix_host.argtypes = [ctypes.c_int] * 8 + [ctypes.c_void_p]
         L.cflx_dbg_gemm_tn.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3 + [ctypes.c_double] * 2 + [
             ctypes.c_void_p, ctypes.c_int, c_double_p]

@@ -98,25 +98,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_kernel(GemmArgs g) {
         if (lane == 0) mbar_arrive(&empty[s]);
     }
 
-    // ===== epilogue: registers <-> HBM directly, 16-byte accesses (each quad covers one 64 B row segment) =====
+    // ===== epilogue: registers <-> HBM directly, 16-byte accesses (each quad covers one 64 B row segment).
+    // C and D may alias, so the compiler must not be left to order loads after earlier stores: all C loads of a
+    // batch of two 8-row slabs are issued first (8 independent 16 B loads in flight per thread), then the stores.
     const double alpha = g.alpha, beta = g.beta;
+    const bool use_c = (beta != 0.0);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int row = m0 + wm_off + 8 * i + g4;
-        if (row >= g.M) continue;
+    for (int ib = 0; ib < 8; ib += 2) {
+        double2 cv[2][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int col = n0 + wn_off + 8 * j + 2 * t4;
-            if (col >= g.N) continue;
-            double2 out;
-            out.x = alpha * acc[i][j][0];
-            out.y = alpha * acc[i][j][1];
-            if (beta != 0.0) {
-                const double2 c = *reinterpret_cast<const double2*>(g.C + (int64_t)row * g.ldc + col);
-                out.x += beta * c.x;
-                out.y += beta * c.y;
+        for (int ii = 0; ii < 2; ++ii) {
+            const int row = m0 + wm_off + 8 * (ib + ii) + g4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col = n0 + wn_off + 8 * j + 2 * t4;
+                cv[ii][j] = make_double2(0.0, 0.0);
+                if (use_c && row < g.M && col < g.N)
+                    cv[ii][j] = __ldg(reinterpret_cast<const double2*>(g.C + (int64_t)row * g.ldc + col));
             }
-            *reinterpret_cast<double2*>(g.D + (int64_t)row * g.ldd + col) = out;
+        }
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii) {
+            const int row = m0 + wm_off + 8 * (ib + ii) + g4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col = n0 + wn_off + 8 * j + 2 * t4;
+                if (row < g.M && col < g.N) {
+                    double2 out;
+                    out.x = fma(alpha, acc[ib + ii][j][0], beta * cv[ii][j].x);
+                    out.y = fma(alpha, acc[ib + ii][j][1], beta * cv[ii][j].y);
+                    *reinterpret_cast<double2*>(g.D + (int64_t)row * g.ldd + col) = out;
+                }
+            }
         }
     }
 }

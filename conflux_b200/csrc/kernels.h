@@ -29,11 +29,8 @@ int launch_gemm_tn(const GemmArgs& g, cudaStream_t stream);
 // multipliers only for the others).  perm_out[0..v) = LAPACK-equivalent winners (row index chosen at step j,
 // identity beyond min(n, v)); see panel.cu for the tie-breaking contract.
 struct PanelWorkspace {
-    double* slot_rows;  // [2][148][32]
-    double* slot_val;   // [2][148]
-    int* slot_pos;      // [2][148]
-    int* slot_row;      // [2][148]
-    int* slot_flag;     // [2][148]
+    void* slot_hdr;     // [2][148][4]  LL words (payload32, epoch)
+    void* slot_rows;    // [2][148][64] LL words
     int epoch;          // host-side running epoch (monotonic across launches)
     int max_ctas;       // co-resident CTA budget (<= 148)
 };

@@ -98,7 +98,8 @@ struct cflx_lu {
     int64_t ldp_max = 0;
     int* h_npiv = nullptr;  // pinned
     std::vector<int> h_hist;
-    bool have_input = false, factored = false, profiling = false;
+    bool have_input = false, factored = false, profiling = false, time_gemm = false;
+    double gemm_ms = 0, gemm_flops = 0;
     int64_t launches = 0;
     double phase_ms[PH_COUNT] = {0};
     std::vector<cudaEvent_t> ev;
@@ -398,7 +399,10 @@ int lu_step(cflx_lu* lu, int k, int& fnpr) {
         g.ldd = Nl;
         g.alpha = -1.0;
         g.beta = 1.0;
+        if (lu->time_gemm) CFLX_CUDA(cudaEventRecord(lu->ev[2 * k], s));
         CFLX_TRY(launch_gemm_tn(g, s));
+        if (lu->time_gemm) CFLX_CUDA(cudaEventRecord(lu->ev[2 * k + 1], s));
+        lu->gemm_flops += 2.0 * g.M * (double)g.N * g.K;
         lu->launches++;
     }
     return CFLX_OK;
@@ -421,7 +425,8 @@ void free_lu(cflx_lu* lu) {
                    lu->idx_buf};
     for (int* p : ints) cudaFree(p);
     if (lu->h_npiv) cudaFreeHost(lu->h_npiv);
-    if (lu->pws.slot_flag) panel_workspace_destroy(&lu->pws);
+    if (lu->pws.slot_hdr) panel_workspace_destroy(&lu->pws);
+    for (auto& e : lu->ev) cudaEventDestroy(e);
     for (SubComm* sc : {&lu->k_comm, &lu->i_comm, &lu->jk_comm, &lu->ik_comm})
         if (sc->c) ncclCommDestroy(sc->c);
     delete lu;
@@ -674,6 +679,12 @@ int cflx_lu_factor(cflx_lu* lu, double* ms_out) {
     CFLX_CUDA(cudaEventCreate(&e1));
     CFLX_CUDA(cudaEventRecord(e0, s));
     int fnpr = 0;
+    lu->gemm_flops = 0;
+    lu->gemm_ms = 0;
+    if (lu->time_gemm && (int)lu->ev.size() < 2 * lu->Nt) {
+        lu->ev.resize(2 * lu->Nt);
+        for (auto& e : lu->ev) CFLX_CUDA(cudaEventCreate(&e));
+    }
     for (int k = 0; k < lu->Nt; ++k) {
         int rc = lu_step(lu, k, fnpr);
         if (rc != CFLX_OK) {
@@ -690,6 +701,13 @@ int cflx_lu_factor(cflx_lu* lu, double* ms_out) {
     cudaEventDestroy(e1);
     CFLX_CUDA(cudaGetLastError());
     if (ms_out) *ms_out = ms;
+    if (lu->time_gemm) {
+        for (int k = 0; k < lu->Nt; ++k) {
+            float g = 0;
+            if (cudaEventElapsedTime(&g, lu->ev[2 * k], lu->ev[2 * k + 1]) == cudaSuccess) lu->gemm_ms += g;
+            else cudaGetLastError();
+        }
+    }
     lu->factored = true;
     return CFLX_OK;
 }
@@ -794,6 +812,17 @@ int cflx_lu_set_profiling(cflx_lu* lu, int enabled) {
 int cflx_lu_phase_ms(cflx_lu* lu, double* ms_out) {
     if (!lu || !ms_out) return CFLX_ERR_ARG;
     for (int i = 0; i < PH_COUNT; ++i) ms_out[i] = lu->phase_ms[i];
+    return CFLX_OK;
+}
+int cflx_lu_set_kernel_timing(cflx_lu* lu, int enabled) {
+    if (!lu) return CFLX_ERR_ARG;
+    lu->time_gemm = enabled != 0;
+    return CFLX_OK;
+}
+int cflx_lu_trailing_stats(cflx_lu* lu, double* ms_out, double* flops_out) {
+    if (!lu || !ms_out || !flops_out) return CFLX_ERR_ARG;
+    *ms_out = lu->gemm_ms;
+    *flops_out = lu->gemm_flops;
     return CFLX_OK;
 }
 void cflx_lu_destroy(cflx_lu* lu) { free_lu(lu); }

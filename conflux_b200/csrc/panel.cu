@@ -39,13 +39,20 @@ struct PanelArgs {
     int R, Rpad, G;
     int* perm_out;
     double* A00;  // may be null: rows of L00\U00 from the pivot's inner block on
-    double* slot_rows;
-    double* slot_val;
-    int* slot_pos;
-    int* slot_row;
-    int* slot_flag;
+    uint2* slot_hdr;   // [2][MAXG][4]  LL words {payload32, epoch}: val_lo, val_hi, pos, row
+    uint2* slot_rows;  // [2][MAXG][64] LL words: inner-block row of the candidate, two words per double
     int epoch_base;
 };
+
+// "LL" exchange (flag travels with the data in one 8-byte word, so no fence / separate flag / L1 invalidate):
+__device__ __forceinline__ void st_ll(uint2* p, unsigned data, unsigned epoch) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ uint4 ld_ll2(const uint2* p) {  // two consecutive LL words
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
 
 struct Cand {
     unsigned long long key;  // bits of |a| (monotone for non-negative doubles)
@@ -71,23 +78,26 @@ __device__ __forceinline__ Cand warp_argmax(Cand c) {
 __device__ __forceinline__ bool better(const Cand& a, const Cand& b) {  // a strictly better than b
     return a.key > b.key || (a.key == b.key && a.pos < b.pos);
 }
-// block-wide argmax; result identical in every thread.  red_* have PT_WARPS entries.
-__device__ __forceinline__ Cand block_argmax(Cand c, unsigned long long* red_key, int* red_pos, int* red_row) {
+// block-wide argmax; result identical in every thread.  red_* have 2 x PT_WARPS entries and `rb` alternates between
+// the two halves on every call, so ONE barrier per reduction is enough (the buffer of call i is rewritten by call
+// i+2, which every thread reaches only after the barrier of call i+1).
+__device__ __forceinline__ Cand block_argmax(Cand c, unsigned long long* red_key, int* red_pos, int* red_row, int& rb) {
     Cand w = warp_argmax(c);
     const int warp = threadIdx.x >> 5;
+    const int o = rb * PT_WARPS;
+    rb ^= 1;
     if ((threadIdx.x & 31) == 0) {
-        red_key[warp] = w.key;
-        red_pos[warp] = w.pos;
-        red_row[warp] = w.row;
+        red_key[o + warp] = w.key;
+        red_pos[o + warp] = w.pos;
+        red_row[o + warp] = w.row;
     }
     __syncthreads();
-    Cand best{red_key[0], red_pos[0], red_row[0]};
+    Cand best{red_key[o], red_pos[o], red_row[o]};
 #pragma unroll
     for (int i = 1; i < PT_WARPS; ++i) {
-        Cand o{red_key[i], red_pos[i], red_row[i]};
-        if (better(o, best)) best = o;
+        Cand x{red_key[o + i], red_pos[o + i], red_row[o + i]};
+        if (better(x, best)) best = x;
     }
-    __syncthreads();  // red_* may be reused right away
     return best;
 }
 
@@ -99,9 +109,10 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
     double* LU11 = U12 + (size_t)NB * p.v;             // [NB][NB+1] LU rows of this block's pivots
     double* prow = LU11 + NB * (NB + 1);               // [NB]
     unsigned long long* red_key = reinterpret_cast<unsigned long long*>(prow + NB);
-    int* red_pos = reinterpret_cast<int*>(red_key + PT_WARPS);
-    int* red_row = red_pos + PT_WARPS;
-    int* pivrow_blk = red_row + PT_WARPS;  // [NB]
+    int* red_pos = reinterpret_cast<int*>(red_key + 2 * PT_WARPS);
+    int* red_row = red_pos + 2 * PT_WARPS;
+    int* pivrow_blk = red_row + 2 * PT_WARPS;  // [NB]
+    int rb = 0;
 
     const int t = threadIdx.x;
     const int cta = blockIdx.x;
@@ -147,35 +158,44 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                     if (better(o, c)) c = o;
                 }
             }
-            const Cand mine = block_argmax(c, red_key, red_pos, red_row);
-            // publish my CTA's candidate and its inner-block row
+            const Cand mine = block_argmax(c, red_key, red_pos, red_row, rb);
+            // publish my CTA's candidate and its inner-block row (LL words, fire and forget)
             const int par = jg & 1;
-            const int myslot = par * MAXG + cta;
-            const int epoch = p.epoch_base + jg + 1;
-            if (mine.row >= 0 && t < nbc) p.slot_rows[(size_t)myslot * 32 + t] = Ab[t * Rpad + (mine.row - row_base)];
-            __syncthreads();
-            if (t == 0) {
-                p.slot_val[myslot] = __longlong_as_double((long long)mine.key);
-                p.slot_pos[myslot] = mine.pos;
-                p.slot_row[myslot] = mine.row;
-                __threadfence();
-                st_release_gpu(&p.slot_flag[myslot], epoch);
+            const unsigned epoch = (unsigned)(p.epoch_base + jg + 1);
+            uint2* myhdr = p.slot_hdr + (size_t)(par * MAXG + cta) * 4;
+            if (t < 4) {
+                const unsigned w = t == 0 ? (unsigned)mine.key : t == 1 ? (unsigned)(mine.key >> 32)
+                                 : t == 2 ? (unsigned)mine.pos : (unsigned)mine.row;
+                st_ll(myhdr + t, w, epoch);
+            }
+            if (mine.row >= 0 && t < nbc) {
+                const unsigned long long x = (unsigned long long)__double_as_longlong(Ab[t * Rpad + (mine.row - row_base)]);
+                uint2* myrow = p.slot_rows + (size_t)(par * MAXG + cta) * 64 + 2 * t;
+                st_ll(myrow, (unsigned)x, epoch);
+                st_ll(myrow + 1, (unsigned)(x >> 32), epoch);
             }
             // gather every CTA's candidate
             Cand gc{0ull, INT_MAX, -1};
             for (int g = t; g < p.G; g += PT_THREADS) {
-                const int s = par * MAXG + g;
-                while (ld_acquire_gpu(&p.slot_flag[s]) != epoch) {
-                }
-                Cand o{(unsigned long long)__double_as_longlong(ld_cg_f64(&p.slot_val[s])), ld_cg_s32(&p.slot_pos[s]),
-                       ld_cg_s32(&p.slot_row[s])};
+                const uint2* h = p.slot_hdr + (size_t)(par * MAXG + g) * 4;
+                uint4 a, b;
+                do {
+                    a = ld_ll2(h);
+                    b = ld_ll2(h + 2);
+                } while (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch);
+                Cand o{((unsigned long long)a.z << 32) | a.x, (int)b.x, (int)b.z};
                 if (better(o, gc)) gc = o;
             }
-            const Cand win = block_argmax(gc, red_key, red_pos, red_row);
+            const Cand win = block_argmax(gc, red_key, red_pos, red_row, rb);
             // (win.row < 0 cannot happen while jg < nsteps = min(n, v): some row is still active)
             const int wcta = win.row / p.R;
             if (t < nbc) {
-                const double x = ld_cg_f64(&p.slot_rows[(size_t)(par * MAXG + wcta) * 32 + t]);
+                const uint2* wr = p.slot_rows + (size_t)(par * MAXG + wcta) * 64 + 2 * t;
+                uint4 a;
+                do {
+                    a = ld_ll2(wr);
+                } while (a.y != epoch || a.w != epoch);
+                const double x = __longlong_as_double((long long)(((unsigned long long)a.z << 32) | a.x));
                 prow[t] = x;
                 LU11[j * (NB + 1) + t] = x;
             }
@@ -283,7 +303,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
 template <int NB>
 size_t panel_smem_bytes(int Rpad, int v) {
     return ((size_t)NB * Rpad + (size_t)NB * v + NB * (NB + 1) + NB) * sizeof(double) +
-           PT_WARPS * (sizeof(unsigned long long) + 2 * sizeof(int)) + NB * sizeof(int) + 64;
+           2 * PT_WARPS * (sizeof(unsigned long long) + 2 * sizeof(int)) + NB * sizeof(int) + 64;
 }
 
 template <int NB>
@@ -306,21 +326,16 @@ int panel_workspace_create(PanelWorkspace* ws) {
     CFLX_CUDA(cudaGetDevice(&dev));
     CFLX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     ws->max_ctas = sms < MAXG ? sms : MAXG;
-    ws->epoch = 0;
-    CFLX_CUDA(cudaMalloc(&ws->slot_rows, sizeof(double) * 2 * MAXG * 32));
-    CFLX_CUDA(cudaMalloc(&ws->slot_val, sizeof(double) * 2 * MAXG));
-    CFLX_CUDA(cudaMalloc(&ws->slot_pos, sizeof(int) * 2 * MAXG));
-    CFLX_CUDA(cudaMalloc(&ws->slot_row, sizeof(int) * 2 * MAXG));
-    CFLX_CUDA(cudaMalloc(&ws->slot_flag, sizeof(int) * 2 * MAXG));
-    CFLX_CUDA(cudaMemset(ws->slot_flag, 0, sizeof(int) * 2 * MAXG));
+    ws->epoch = 1;
+    CFLX_CUDA(cudaMalloc(&ws->slot_hdr, sizeof(uint2) * 2 * MAXG * 4));
+    CFLX_CUDA(cudaMalloc(&ws->slot_rows, sizeof(uint2) * 2 * MAXG * 64));
+    CFLX_CUDA(cudaMemset(ws->slot_hdr, 0, sizeof(uint2) * 2 * MAXG * 4));
+    CFLX_CUDA(cudaMemset(ws->slot_rows, 0, sizeof(uint2) * 2 * MAXG * 64));
     return CFLX_OK;
 }
 void panel_workspace_destroy(PanelWorkspace* ws) {
+    cudaFree(ws->slot_hdr);
     cudaFree(ws->slot_rows);
-    cudaFree(ws->slot_val);
-    cudaFree(ws->slot_pos);
-    cudaFree(ws->slot_row);
-    cudaFree(ws->slot_flag);
     *ws = PanelWorkspace{};
 }
 
@@ -350,11 +365,8 @@ int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, 
     a.G = G;
     a.perm_out = perm_out;
     a.A00 = A00;
-    a.slot_rows = ws->slot_rows;
-    a.slot_val = ws->slot_val;
-    a.slot_pos = ws->slot_pos;
-    a.slot_row = ws->slot_row;
-    a.slot_flag = ws->slot_flag;
+    a.slot_hdr = reinterpret_cast<uint2*>(ws->slot_hdr);
+    a.slot_rows = reinterpret_cast<uint2*>(ws->slot_rows);
     a.epoch_base = ws->epoch;
     ws->epoch += v + 2 + (v & 1);  // keep the base even so slot parity == column parity
     const size_t budget = 200 * 1024;

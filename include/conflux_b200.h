@@ -83,6 +83,10 @@ int cflx_lu_launch_count(cflx_lu*, int64_t* count_out, int reset);
  * {panel, tournament+bcast, row moves, reduce+gather, trsm, gemm, stores, other} */
 int cflx_lu_set_profiling(cflx_lu*, int enabled);
 int cflx_lu_phase_ms(cflx_lu*, double* ms_out);
+/* CUDA-event timing of the dominant kernel (the trailing-update DGEMM launches of the last cflx_lu_factor, events
+ * recorded on the launching stream): summed device ms and the algorithmic flops 2*m*n*k of those launches */
+int cflx_lu_set_kernel_timing(cflx_lu*, int enabled);
+int cflx_lu_trailing_stats(cflx_lu*, double* ms_out, double* flops_out);
 void cflx_lu_destroy(cflx_lu*);
 
 /* ---- single-device building blocks exposed for tests and micro-benchmarks (host buffers in, host out) ----- */
