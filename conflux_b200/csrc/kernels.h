@@ -33,6 +33,7 @@ struct PanelWorkspace {
     void* slot_rows;    // [2][148][64] LL words
     int epoch;          // host-side running epoch (monotonic across launches)
     int max_ctas;       // co-resident CTA budget (<= 148)
+    int cta_cap;        // optional cap on the grid (look-ahead: leave SMs to the trailing update); 0 = none
 };
 int panel_workspace_create(PanelWorkspace* ws);
 void panel_workspace_destroy(PanelWorkspace* ws);

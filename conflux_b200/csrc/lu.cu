@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <vector>
@@ -103,6 +104,9 @@ struct cflx_lu {
     int64_t launches = 0;
     double phase_ms[PH_COUNT] = {0};
     std::vector<cudaEvent_t> ev;
+    std::vector<char> ev_used;
+    cudaStream_t side = nullptr;  // high-priority look-ahead stream (null: no overlap)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -216,7 +220,104 @@ __global__ void scatter_rows_kernel(const double* __restrict__ in, int ncols, co
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += gridDim.x * blockDim.x) d[c] = s[c];
 }
 
-int lu_step(cflx_lu* lu, int k, int& fnpr) {
+// ---- steps 0 + 1 of iteration k: panel extract (+ layer reduce), local pivot search, tournament.  Runs on stream
+// `s`; with look-ahead that is the high-priority side stream and overlaps the trailing update of iteration k-1.
+// Touches only: PT, W, perm, candH/tagsH/S/W2/tagsS, A00/A00T (outputs consumed by finish_step(k) after the join).
+int panel_phase(cflx_lu* lu, int k, int fnpr, cudaStream_t s) {
+    const int v = lu->v, Px = lu->Px, Py = lu->Py, Pz = lu->Pz, Ml = lu->Ml, Nl = lu->Nl;
+    const int pi = lu->pi, pj = lu->pj, pk = lu->pk;
+    const int loff = (k / Py) * v, pjk = k % Py;
+    if (pj != pjk) return CFLX_OK;
+    const int n_old = Ml - fnpr;
+    const int64_t ldk = std::max<int64_t>(2, round_up(n_old, 2));
+    int nR = 0;
+    while ((1 << nR) < Px) ++nR;
+    // ---- step 0: panel extract (+ reduce over layers onto pk = 0)            conflux_opt.hpp:618-648
+    {
+        PhaseTimer t(lu, PH_PANEL);
+        CFLX_TRY(launch_extract_panel_T(lu->A11, Nl, fnpr, loff, n_old, v, lu->PT, ldk, s));
+        lu->launches++;
+        if (Pz > 1 && n_old > 0)
+            CFLX_NCCL(ncclReduce(lu->PT, lu->PT, (size_t)v * ldk, ncclDouble, ncclSum, 0, lu->k_comm.c, s));
+    }
+    if (pk != 0) return CFLX_OK;
+    // ---- step 1: local pivot search + tournament on column pj == k % Py, layer 0   conflux_opt.hpp:693-816
+    int my_half = 0;
+    {
+        PhaseTimer t(lu, PH_PANEL);
+        CFLX_CUDA(cudaMemcpyAsync(lu->W, lu->PT, (size_t)v * ldk * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        int nb_used = 0;
+        if (nR == 0) {  // the local search already is the tournament: A00 comes from it
+            CFLX_TRY(launch_panel_getrf_a00(lu->W, ldk, n_old, v, lu->perm, lu->A00, &nb_used, &lu->pws, s));
+            CFLX_TRY(launch_gather_a00(lu->W, ldk, lu->perm, v, nb_used, lu->A00, lu->A00T, s));
+            lu->launches += 2;
+        } else {
+            CFLX_TRY(launch_panel_getrf(lu->W, ldk, n_old, v, lu->perm, &lu->pws, s));
+            lu->launches++;
+        }
+        int first_partner = flipbit(pi, 0);
+        if (first_partner > Px - 1) first_partner = Px - 1;
+        my_half = first_partner < pi ? 1 : 0;  // "higher rank puts his candidates below" (conflux_opt.hpp:717-750)
+        CFLX_TRY(launch_gather_winners(lu->PT, ldk, lu->gri + fnpr, n_old, lu->perm, v,
+                                       lu->candH + (size_t)my_half * v * v, v, lu->tagsH + my_half * v, 0, s));
+        lu->launches++;
+    }
+    PhaseTimer t(lu, PH_TOURN);
+    for (int r = 0; r < nR; ++r) {
+        CFLX_TRY(tournament_exchange(lu, r, my_half, s));
+        const int64_t tot = (int64_t)2 * v * v;
+        stack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(lu->candH, lu->tagsH, v, lu->S, lu->W2, lu->tagsS);
+        CFLX_CUDA(cudaGetLastError());
+        const bool last = (r == nR - 1);
+        int nb_used = 0;
+        if (last) {
+            CFLX_TRY(launch_panel_getrf_a00(lu->W2, 2 * v, 2 * v, v, lu->perm, lu->A00, &nb_used, &lu->pws, s));
+            CFLX_TRY(launch_gather_a00(lu->W2, 2 * v, lu->perm, v, nb_used, lu->A00, lu->A00T, s));
+            lu->launches++;
+            my_half = 0;
+        } else {
+            CFLX_TRY(launch_panel_getrf(lu->W2, 2 * v, 2 * v, v, lu->perm, &lu->pws, s));
+            my_half = butterfly_pair(pi, r + 1, Px) < pi ? 1 : 0;
+        }
+        CFLX_TRY(launch_gather_winners(lu->S, 2 * v, lu->tagsS, 2 * v, lu->perm, v, lu->candH + (size_t)my_half * v * v,
+                                       v, lu->tagsH + my_half * v, 0, s));
+        lu->launches += 3;
+    }
+    // winners now sit in the upper half: tagsH[0..v) = global pivot rows (conflux_opt.hpp:810-815)
+    return CFLX_OK;
+}
+
+int trailing_gemm(cflx_lu* lu, int k, int part, int fnpr, int n_act, int col_lo, int ncols, int64_t ld2, int64_t ldu,
+                  int u_col_off, cudaStream_t s) {
+    if (n_act <= 0 || ncols <= 0) return CFLX_OK;
+    PhaseTimer t(lu, PH_GEMM);
+    GemmArgs g{};
+    g.M = n_act;
+    g.N = ncols;
+    g.K = lu->nlayr;
+    g.AT = lu->LT + (int64_t)lu->pk * lu->nlayr * ld2;
+    g.ldat = ld2;
+    g.B = lu->U + (int64_t)lu->pk * lu->nlayr * ldu + u_col_off;
+    g.ldb = ldu;
+    g.C = lu->A11 + (int64_t)fnpr * lu->Nl + col_lo;
+    g.ldc = lu->Nl;
+    g.D = lu->A11 + (int64_t)fnpr * lu->Nl + col_lo;
+    g.ldd = lu->Nl;
+    g.alpha = -1.0;
+    g.beta = 1.0;
+    const int e = 4 * k + 2 * part;
+    if (lu->time_gemm) CFLX_CUDA(cudaEventRecord(lu->ev[e], s));
+    CFLX_TRY(launch_gemm_tn(g, s));
+    if (lu->time_gemm) CFLX_CUDA(cudaEventRecord(lu->ev[e + 1], s));
+    lu->ev_used[e / 2] = lu->time_gemm;
+    lu->gemm_flops += 2.0 * g.M * (double)g.N * g.K;
+    lu->launches++;
+    return CFLX_OK;
+}
+
+// ---- everything of iteration k after the pivot search: pivot broadcast, row moves, solves, stores, trailing update
+// (with the columns of panel k+1 updated first so that panel_phase(k+1) can start on the side stream).
+int finish_step(cflx_lu* lu, int k, int& fnpr) {
     cudaStream_t s = lu->comm->stream;
     const int v = lu->v, Px = lu->Px, Py = lu->Py, Pz = lu->Pz, Ml = lu->Ml, Nl = lu->Nl;
     const int pi = lu->pi, pj = lu->pj, pk = lu->pk;
@@ -229,60 +330,6 @@ int lu_step(cflx_lu* lu, int k, int& fnpr) {
     const int64_t ldk = std::max<int64_t>(2, round_up(n_old, 2));
     int nR = 0;
     while ((1 << nR) < Px) ++nR;
-
-    // ---- step 0: panel extract (+ reduce over layers onto pk = 0)            conflux_opt.hpp:618-648
-    if (on_col) {
-        PhaseTimer t(lu, PH_PANEL);
-        CFLX_TRY(launch_extract_panel_T(lu->A11, Nl, fnpr_old, loff, n_old, v, lu->PT, ldk, s));
-        lu->launches++;
-        if (Pz > 1 && n_old > 0)
-            CFLX_NCCL(ncclReduce(lu->PT, lu->PT, (size_t)v * ldk, ncclDouble, ncclSum, 0, lu->k_comm.c, s));
-    }
-    // ---- step 1: local pivot search + tournament on column pj == k % Py, layer 0   conflux_opt.hpp:693-816
-    if (on_col && layer0) {
-        int my_half = 0;
-        {
-            PhaseTimer t(lu, PH_PANEL);
-            CFLX_CUDA(cudaMemcpyAsync(lu->W, lu->PT, (size_t)v * ldk * sizeof(double), cudaMemcpyDeviceToDevice, s));
-            int nb_used = 0;
-            if (nR == 0) {  // the local search already is the tournament: A00 comes from it
-                CFLX_TRY(launch_panel_getrf_a00(lu->W, ldk, n_old, v, lu->perm, lu->A00, &nb_used, &lu->pws, s));
-                CFLX_TRY(launch_gather_a00(lu->W, ldk, lu->perm, v, nb_used, lu->A00, lu->A00T, s));
-                lu->launches += 2;
-            } else {
-                CFLX_TRY(launch_panel_getrf(lu->W, ldk, n_old, v, lu->perm, &lu->pws, s));
-                lu->launches++;
-            }
-            int first_partner = flipbit(pi, 0);
-            if (first_partner > Px - 1) first_partner = Px - 1;
-            my_half = first_partner < pi ? 1 : 0;  // "higher rank puts his candidates below" (conflux_opt.hpp:717-750)
-            CFLX_TRY(launch_gather_winners(lu->PT, ldk, lu->gri + fnpr_old, n_old, lu->perm, v,
-                                           lu->candH + (size_t)my_half * v * v, v, lu->tagsH + my_half * v, 0, s));
-            lu->launches++;
-        }
-        PhaseTimer t(lu, PH_TOURN);
-        for (int r = 0; r < nR; ++r) {
-            CFLX_TRY(tournament_exchange(lu, r, my_half, s));
-            const int64_t tot = (int64_t)2 * v * v;
-            stack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(lu->candH, lu->tagsH, v, lu->S, lu->W2, lu->tagsS);
-            CFLX_CUDA(cudaGetLastError());
-            const bool last = (r == nR - 1);
-            int nb_used = 0;
-            if (last) {
-                CFLX_TRY(launch_panel_getrf_a00(lu->W2, 2 * v, 2 * v, v, lu->perm, lu->A00, &nb_used, &lu->pws, s));
-                CFLX_TRY(launch_gather_a00(lu->W2, 2 * v, lu->perm, v, nb_used, lu->A00, lu->A00T, s));
-                lu->launches++;
-                my_half = 0;
-            } else {
-                CFLX_TRY(launch_panel_getrf(lu->W2, 2 * v, 2 * v, v, lu->perm, &lu->pws, s));
-                my_half = butterfly_pair(pi, r + 1, Px) < pi ? 1 : 0;
-            }
-            CFLX_TRY(launch_gather_winners(lu->S, 2 * v, lu->tagsS, 2 * v, lu->perm, v,
-                                           lu->candH + (size_t)my_half * v * v, v, lu->tagsH + my_half * v, 0, s));
-            lu->launches += 3;
-        }
-        // winners now sit in the upper half: tagsH[0..v) = global pivot rows (conflux_opt.hpp:810-815)
-    }
     // ---- A00 + pivot ids to everybody (one broadcast)                     conflux_opt.hpp:818-850,872
     {
         PhaseTimer t(lu, PH_TOURN);
@@ -332,9 +379,13 @@ int lu_step(cflx_lu* lu, int k, int& fnpr) {
     const int n_act = Ml - fnpr;
     const int64_t ld2 = std::max<int64_t>(2, round_up(n_act, 2));
     const int64_t ldu = std::max(2, ncols);
+    // At Px == 1 the local pivot search IS the panel factorisation: its multipliers are the L panel (same values a
+    // LAPACK getrf leaves behind; the reference recomputes them with dtrsm against A00, conflux_opt.hpp:1347).
+    const bool fused_l = (nR == 0);
     if (on_col && layer0 && n_act > 0) {
         PhaseTimer t(lu, PH_MOVES);
-        CFLX_TRY(launch_compact_panel(lu->PT, ldk, lu->PT2, ld2, lu->plan.rowsrc, fnpr_old, lu->plan.npiv, Ml, v, s));
+        CFLX_TRY(launch_compact_panel(fused_l ? lu->W : lu->PT, ldk, fused_l ? lu->LT : lu->PT2, ld2, lu->plan.rowsrc,
+                                      fnpr_old, lu->plan.npiv, Ml, v, s));
         lu->launches++;
     }
     // ---- steps 2b/3: pivot rows summed over layers and gathered on row pi == k % Px   conflux_opt.hpp:1164-1260
@@ -343,13 +394,13 @@ int lu_step(cflx_lu* lu, int k, int& fnpr) {
         CFLX_NCCL(ncclReduce(lu->A01raw, lu->A01raw, (size_t)v * ldu, ncclDouble, ncclSum, pik * Pz, lu->ik_comm.c, s));
     }
     // ---- steps 4/5: the two triangular solves                              conflux_opt.hpp:1329-1359,1522-1551
-    if (layer0 && (on_col || on_row)) {
+    if (layer0 && ((on_col && !fused_l) || on_row)) {
         PhaseTimer t(lu, PH_TRSM);
         CFLX_TRY(launch_diag_inverses(lu->A00, v, lu->nb, lu->Uinv, lu->LinvT, s));
         lu->launches++;
     }
     if (on_col && layer0 && n_act > 0) {
-        {
+        if (!fused_l) {
             PhaseTimer t(lu, PH_TRSM);
             CFLX_TRY(trsm_right_upper_T(lu->A00, lu->Uinv, v, lu->nb, lu->PT2, lu->LT, ld2, n_act, s));
             lu->launches += 2 * (v / lu->nb) - 1;
@@ -383,27 +434,24 @@ int lu_step(cflx_lu* lu, int k, int& fnpr) {
         }
     }
     // ---- step 6: trailing update on every rank and layer                    conflux_opt.hpp:1628-1632
-    if (n_act > 0 && ncols > 0) {
-        PhaseTimer t(lu, PH_GEMM);
-        GemmArgs g{};
-        g.M = n_act;
-        g.N = ncols;
-        g.K = lu->nlayr;
-        g.AT = lu->LT + (int64_t)pk * lu->nlayr * ld2;
-        g.ldat = ld2;
-        g.B = lu->U + (int64_t)pk * lu->nlayr * ldu;
-        g.ldb = ldu;
-        g.C = lu->A11 + (int64_t)fnpr * Nl + c0;
-        g.ldc = Nl;
-        g.D = lu->A11 + (int64_t)fnpr * Nl + c0;
-        g.ldd = Nl;
-        g.alpha = -1.0;
-        g.beta = 1.0;
-        if (lu->time_gemm) CFLX_CUDA(cudaEventRecord(lu->ev[2 * k], s));
-        CFLX_TRY(launch_gemm_tn(g, s));
-        if (lu->time_gemm) CFLX_CUDA(cudaEventRecord(lu->ev[2 * k + 1], s));
-        lu->gemm_flops += 2.0 * g.M * (double)g.N * g.K;
-        lu->launches++;
+    // Look-ahead: the rank that owns panel k+1 updates those v columns first (they are its first live block), forks
+    // the pivot search of iteration k+1 onto the side stream, and only then updates the remaining columns.
+    const bool next_col = (k + 1 < lu->Nt) && (pj == (k + 1) % Py);
+    if (next_col) {
+        const int w = std::min(v, ncols);
+        CFLX_TRY(trailing_gemm(lu, k, 0, fnpr, n_act, c0, w, ld2, ldu, 0, s));
+        cudaStream_t side = lu->profiling ? nullptr : lu->side;  // phase profiling serialises everything
+        cudaStream_t sp = side ? side : s;
+        if (side) {
+            CFLX_CUDA(cudaEventRecord(lu->ev_fork, s));
+            CFLX_CUDA(cudaStreamWaitEvent(sp, lu->ev_fork, 0));
+        }
+        CFLX_TRY(panel_phase(lu, k + 1, fnpr, sp));
+        if (side) CFLX_CUDA(cudaEventRecord(lu->ev_join, sp));
+        CFLX_TRY(trailing_gemm(lu, k, 1, fnpr, n_act, c0 + w, ncols - w, ld2, ldu, w, s));
+        if (side) CFLX_CUDA(cudaStreamWaitEvent(s, lu->ev_join, 0));
+    } else {
+        CFLX_TRY(trailing_gemm(lu, k, 0, fnpr, n_act, c0, ncols, ld2, ldu, 0, s));
     }
     return CFLX_OK;
 }
@@ -427,6 +475,9 @@ void free_lu(cflx_lu* lu) {
     if (lu->h_npiv) cudaFreeHost(lu->h_npiv);
     if (lu->pws.slot_hdr) panel_workspace_destroy(&lu->pws);
     for (auto& e : lu->ev) cudaEventDestroy(e);
+    if (lu->side) cudaStreamDestroy(lu->side);
+    if (lu->ev_fork) cudaEventDestroy(lu->ev_fork);
+    if (lu->ev_join) cudaEventDestroy(lu->ev_join);
     for (SubComm* sc : {&lu->k_comm, &lu->i_comm, &lu->jk_comm, &lu->ik_comm})
         if (sc->c) ncclCommDestroy(sc->c);
     delete lu;
@@ -627,6 +678,22 @@ int cflx_lu_create(cflx_comm* c, int M, int N, int v, int Px, int Py, int Pz, cf
     if ((rc = panel_workspace_create(&lu->pws))) return fail(rc);
     if ((rc = gemm_tn_setup())) return fail(rc);
     lu->h_hist.assign(lu->M, -1);
+    {
+        // look-ahead: pivot search of iteration k+1 on a high-priority side stream, on a capped number of SMs, while
+        // the trailing update of iteration k runs on the rest.  (Enabled on single-rank grids; multi-rank grids keep
+        // one stream so that all NCCL calls of a rank stay in one order.)
+        const char* e = getenv("CFLX_LOOKAHEAD");
+        const bool want = e ? atoi(e) != 0 : true;
+        if (want && lu->P == 1) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            if (cudaStreamCreateWithPriority(&lu->side, cudaStreamNonBlocking, hi) != cudaSuccess) return fail(CFLX_ERR_CUDA);
+            if (cudaEventCreateWithFlags(&lu->ev_fork, cudaEventDisableTiming) != cudaSuccess) return fail(CFLX_ERR_CUDA);
+            if (cudaEventCreateWithFlags(&lu->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail(CFLX_ERR_CUDA);
+            const char* c = getenv("CFLX_PANEL_CTAS");
+            lu->pws.cta_cap = c ? atoi(c) : 32;
+        }
+    }
     // zero the panels once: padded columns are read (and masked) by the GEMM producer
     cudaMemsetAsync(lu->PT, 0, pan * sizeof(double), c->stream);
     cudaMemsetAsync(lu->PT2, 0, pan * sizeof(double), c->stream);
@@ -681,12 +748,19 @@ int cflx_lu_factor(cflx_lu* lu, double* ms_out) {
     int fnpr = 0;
     lu->gemm_flops = 0;
     lu->gemm_ms = 0;
-    if (lu->time_gemm && (int)lu->ev.size() < 2 * lu->Nt) {
-        lu->ev.resize(2 * lu->Nt);
+    if (lu->time_gemm && (int)lu->ev.size() < 4 * lu->Nt) {
+        for (auto& e : lu->ev) cudaEventDestroy(e);
+    if (lu->side) cudaStreamDestroy(lu->side);
+    if (lu->ev_fork) cudaEventDestroy(lu->ev_fork);
+    if (lu->ev_join) cudaEventDestroy(lu->ev_join);
+        lu->ev.assign(4 * lu->Nt, nullptr);
         for (auto& e : lu->ev) CFLX_CUDA(cudaEventCreate(&e));
     }
+    lu->ev_used.assign(2 * lu->Nt, 0);
+    int rc0 = panel_phase(lu, 0, 0, s);
+    if (rc0 != CFLX_OK) return rc0;
     for (int k = 0; k < lu->Nt; ++k) {
-        int rc = lu_step(lu, k, fnpr);
+        int rc = finish_step(lu, k, fnpr);
         if (rc != CFLX_OK) {
             cudaEventDestroy(e0);
             cudaEventDestroy(e1);
@@ -702,9 +776,10 @@ int cflx_lu_factor(cflx_lu* lu, double* ms_out) {
     CFLX_CUDA(cudaGetLastError());
     if (ms_out) *ms_out = ms;
     if (lu->time_gemm) {
-        for (int k = 0; k < lu->Nt; ++k) {
+        for (int i = 0; i < 2 * lu->Nt; ++i) {
+            if (!lu->ev_used[i]) continue;
             float g = 0;
-            if (cudaEventElapsedTime(&g, lu->ev[2 * k], lu->ev[2 * k + 1]) == cudaSuccess) lu->gemm_ms += g;
+            if (cudaEventElapsedTime(&g, lu->ev[2 * i], lu->ev[2 * i + 1]) == cudaSuccess) lu->gemm_ms += g;
             else cudaGetLastError();
         }
     }

@@ -30,7 +30,7 @@ namespace {
 constexpr int PT_THREADS = 128;
 constexpr int PT_WARPS = PT_THREADS / 32;
 constexpr int MAXG = 148;
-constexpr int RPT_MAX = 4;  // rows per thread -> R <= 512 rows per CTA
+constexpr int RPT_MAX = 8;  // rows per thread -> R <= 1024 rows per CTA
 
 struct PanelArgs {
     double* W;
@@ -245,26 +245,30 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
         const int rem = v - cstart;
         if (rem > 0) {
             __syncthreads();  // pivrow_blk, LU11 complete
-            for (int e = t; e < nsb * rem; e += PT_THREADS) {
-                const int i = e / rem, cc = e % rem;
-                U12[i * v + cc] = ld_cg_f64(&W[(int64_t)(cstart + cc) * ldw + pivrow_blk[i]]);
-            }
-            __syncthreads();
-            for (int cc = t; cc < rem; cc += PT_THREADS) {  // unit-lower forward substitution, one column per thread
-                for (int i = 1; i < nsb; ++i) {
-                    double u = U12[i * v + cc];
-                    for (int s2 = 0; s2 < i; ++s2) u -= LU11[i * (NB + 1) + s2] * U12[s2 * v + cc];
-                    U12[i * v + cc] = u;
-                }
-            }
-            __syncthreads();
-            if (cta == 0 && p.A00 != nullptr) {
-                for (int e = t; e < nsb * rem; e += PT_THREADS) {
-                    const int i = e / rem, cc = e % rem;
-                    p.A00[(size_t)(jb + i) * v + cstart + cc] = U12[i * v + cc];
-                }
-            }
+            // one trailing column per thread: NB independent scattered loads in flight, then the unit-lower forward
+            // substitution entirely in registers (L11 broadcast from shared memory)
+            for (int cc = t; cc < rem; cc += PT_THREADS) {
+                const double* col = W + (int64_t)(cstart + cc) * ldw;
+                double u[NB];
 #pragma unroll
+                for (int i = 0; i < NB; ++i) u[i] = (i < nsb) ? ld_cg_f64(col + pivrow_blk[i]) : 0.0;
+#pragma unroll
+                for (int i = 1; i < NB; ++i) {
+                    if (i < nsb) {
+#pragma unroll
+                        for (int s2 = 0; s2 < i; ++s2) u[i] -= LU11[i * (NB + 1) + s2] * u[s2];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NB; ++i) U12[i * v + cc] = u[i];
+                if (cta == 0 && p.A00 != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < NB; ++i)
+                        if (i < nsb) p.A00[(size_t)(jb + i) * v + cstart + cc] = u[i];
+                }
+            }
+            __syncthreads();
+#pragma unroll 1
             for (int q = 0; q < RPT_MAX; ++q) {
                 const int lr = t + q * PT_THREADS;
                 if (lr >= Rloc || !active[q]) continue;  // finished pivot rows are never read again
@@ -273,17 +277,24 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                 for (int i = 0; i < NB; ++i) l[i] = (i < nsb) ? Ab[i * Rpad + lr] : 0.0;
                 double* wp = W + (int64_t)cstart * ldw + row_base + lr;
                 int cc = 0;
-                for (; cc + 1 < rem; cc += 2) {
+                for (; cc + 3 < rem; cc += 4) {  // 4 independent global loads in flight, U12 read as 2 x LDS.128
                     double w0 = wp[(int64_t)cc * ldw], w1 = wp[(int64_t)(cc + 1) * ldw];
+                    double w2 = wp[(int64_t)(cc + 2) * ldw], w3 = wp[(int64_t)(cc + 3) * ldw];
 #pragma unroll
                     for (int i = 0; i < NB; ++i) {
-                        w0 -= l[i] * U12[i * v + cc];
-                        w1 -= l[i] * U12[i * v + cc + 1];
+                        const double2 ua = *reinterpret_cast<const double2*>(U12 + i * v + cc);
+                        const double2 ub = *reinterpret_cast<const double2*>(U12 + i * v + cc + 2);
+                        w0 -= l[i] * ua.x;
+                        w1 -= l[i] * ua.y;
+                        w2 -= l[i] * ub.x;
+                        w3 -= l[i] * ub.y;
                     }
                     wp[(int64_t)cc * ldw] = w0;
                     wp[(int64_t)(cc + 1) * ldw] = w1;
+                    wp[(int64_t)(cc + 2) * ldw] = w2;
+                    wp[(int64_t)(cc + 3) * ldw] = w3;
                 }
-                if (cc < rem) {
+                for (; cc < rem; ++cc) {
                     double w0 = wp[(int64_t)cc * ldw];
 #pragma unroll
                     for (int i = 0; i < NB; ++i) w0 -= l[i] * U12[i * v + cc];
@@ -327,6 +338,7 @@ int panel_workspace_create(PanelWorkspace* ws) {
     CFLX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     ws->max_ctas = sms < MAXG ? sms : MAXG;
     ws->epoch = 1;
+    ws->cta_cap = 0;
     CFLX_CUDA(cudaMalloc(&ws->slot_hdr, sizeof(uint2) * 2 * MAXG * 4));
     CFLX_CUDA(cudaMalloc(&ws->slot_rows, sizeof(uint2) * 2 * MAXG * 64));
     CFLX_CUDA(cudaMemset(ws->slot_hdr, 0, sizeof(uint2) * 2 * MAXG * 4));
@@ -353,6 +365,7 @@ int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, 
     int G = (n + PT_THREADS - 1) / PT_THREADS;
     if (G < 1) G = 1;
     if (G > ws->max_ctas) G = ws->max_ctas;
+    if (ws->cta_cap > 0 && G > ws->cta_cap) G = ws->cta_cap;
     int R = (n + G - 1) / G;
     R = (int)round_up(R > 0 ? R : 1, 32);
     G = n > 0 ? (n + R - 1) / R : 1;
@@ -369,7 +382,7 @@ int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, 
     a.slot_rows = reinterpret_cast<uint2*>(ws->slot_rows);
     a.epoch_base = ws->epoch;
     ws->epoch += v + 2 + (v & 1);  // keep the base even so slot parity == column parity
-    const size_t budget = 200 * 1024;
+    const size_t budget = 222 * 1024;
     int nb = v >= 32 ? 32 : (v >= 16 ? 16 : (v >= 8 ? 8 : 4));
     if (nb == 32 && panel_smem_bytes<32>(a.Rpad, v) > budget) nb = 16;
     if (nb == 16 && panel_smem_bytes<16>(a.Rpad, v) > budget) nb = 8;

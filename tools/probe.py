@@ -12,12 +12,15 @@ for (M, N, K) in [(4096, 4096, 256), (8192, 8192, 256), (16128, 16128, 256), (81
     AT, B = rng.standard_normal((K, M)), rng.standard_normal((K, N))
     _, ms = cb.dbg.gemm_tn(AT, B, None, -1.0, 1.0, reps=5)
     print(f"gemm_tn M={M} N={N} K={K}: {ms:.3f} ms  {2.0*M*N*K/ms/1e9:.2f} TFLOP/s", flush=True)
-for (n, v) in [(2048, 256), (16384, 256), (8192, 256), (32768, 512), (1024, 512), (16384, 128)]:
+for (n, v) in [(2048, 256), (16384, 256), (32768, 512), (1024, 512)]:
     P = 5.0 + rng.random((n, v))
     _, _, _, ms = cb.dbg.panel(P, reps=3)
     print(f"panel n={n} v={v}: {ms:.3f} ms ({ms/v*1e3:.2f} us/column)", flush=True)
 comm = cb.Comm(1, 0, None, 0)
-for (N, v) in [(2048, 128), (4096, 256), (8192, 256), (16384, 256)]:
+cfgs = [(la, ctas, N, v) for (N, v) in [(4096, 256), (8192, 256), (16384, 256)] for (la, ctas) in [(0, 0), (1, 16), (1, 32), (1, 64)]]
+for (la, ctas, N, v) in cfgs:
+    os.environ["CFLX_LOOKAHEAD"] = str(la)
+    os.environ["CFLX_PANEL_CTAS"] = str(ctas)
     gv = cb.lu_params(N, N, v, 1, 1, 1, comm)
     perm = np.zeros(gv.M, dtype=np.int32)
     cb.LU_rep(gv, None, perm)
@@ -29,7 +32,7 @@ for (N, v) in [(2048, 128), (4096, 256), (8192, 256), (16384, 256)]:
     ph = (ctypes.c_double * 8)()
     cb._lib.lib().cflx_lu_phase_ms(gv._h, ph)
     cb._lib.lib().cflx_lu_set_profiling(gv._h, 0)
-    print(f"LU N={N} v={v}: {ms:.2f} ms  {2/3*N**3/ms/1e9:.2f} TFLOP/s   phases(ms, serialised): " +
+    print(f"LU lookahead={la} panel_ctas={ctas} N={N} v={v}: {ms:.2f} ms  {2/3*N**3/ms/1e9:.2f} TFLOP/s   phases(ms, serialised): " +
           ", ".join(f"{n}={x:.1f}" for n, x in zip(["panel", "tourn", "moves", "reduce", "trsm", "gemm", "store", "other"], ph)),
           flush=True)
     gv.free_comms()
