@@ -61,21 +61,28 @@ __global__ void dfma_peak_kernel(double* out, int iters) {
 }
 }  // namespace
 
+static long long g_panel_cycles[8] = {0};
+
 extern "C" {
+
+int cflx_dbg_last_panel_cycles(long long* out8) {
+    for (int i = 0; i < 8; ++i) out8[i] = g_panel_cycles[i];
+    return CFLX_OK;
+}
 
 int cflx_dbg_fp64_peak(int which, double* tflops_out) {
     CFLX_TRY(check_device());
     int dev = 0, sms = 0;
     CFLX_CUDA(cudaGetDevice(&dev));
     CFLX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int threads = 256, blocks = sms * 4, iters = 4096;
+    const int threads = 256, blocks = sms * 4, iters = 16384;
     DevBuf out;
     CFLX_TRY(out.alloc(sizeof(double) * threads * blocks));
     cudaEvent_t e0, e1;
     CFLX_CUDA(cudaEventCreate(&e0));
     CFLX_CUDA(cudaEventCreate(&e1));
     double best = 0;
-    for (int rep = 0; rep < 5; ++rep) {
+    for (int rep = 0; rep < 6; ++rep) {
         CFLX_CUDA(cudaEventRecord(e0));
         if (which == 0) dmma_peak_kernel<<<blocks, threads>>>(out.as<double>(), iters);
         else dfma_peak_kernel<<<blocks, threads>>>(out.as<double>(), iters);
@@ -176,6 +183,7 @@ int cflx_dbg_panel(int n, int v, const double* panel, int* perm_out, double* A00
     cudaEventDestroy(e1);
     if (rc == CFLX_OK && n >= v)
         rc = launch_gather_a00(dW.as<double>(), ld, dperm.as<int>(), v, nb, dA00.as<double>(), dA00T.as<double>(), 0);
+    cudaMemcpy(g_panel_cycles, ws.dbg, sizeof(g_panel_cycles), cudaMemcpyDeviceToHost);
     panel_workspace_destroy(&ws);
     if (rc != CFLX_OK) {
         if (rc == CFLX_ERR_CUDA) set_last_error("panel kernel failed: %s", cudaGetErrorString(cudaGetLastError()));

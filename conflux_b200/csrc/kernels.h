@@ -31,6 +31,7 @@ int launch_gemm_tn(const GemmArgs& g, cudaStream_t stream);
 struct PanelWorkspace {
     void* slot_hdr;     // [2][148][4]  LL words (payload32, epoch)
     void* slot_rows;    // [2][148][64] LL words
+    long long* dbg;     // [8] cycle counters of CTA 0 of the last launch (profiling aid)
     int epoch;          // host-side running epoch (monotonic across launches)
     int max_ctas;       // co-resident CTA budget (<= 148)
     int cta_cap;        // optional cap on the grid (look-ahead: leave SMs to the trailing update); 0 = none

@@ -42,6 +42,8 @@ struct PanelArgs {
     uint2* slot_hdr;   // [2][MAXG][4]  LL words {payload32, epoch}: val_lo, val_hi, pos, row
     uint2* slot_rows;  // [2][MAXG][64] LL words: inner-block row of the candidate, two words per double
     int epoch_base;
+    long long* dbg;    // optional: 8 cycle counters of CTA 0 (cand+argmax, exchange, argmax2, row fetch, eliminate,
+                       // load/write-back, U12 gather+solve, rank update)
 };
 
 // "LL" exchange (flag travels with the data in one 8-byte word, so no fence / separate flag / L1 invalidate):
@@ -122,6 +124,12 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
     double* __restrict__ W = p.W;
     const int64_t ldw = p.ldw;
 
+    long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t0 = clock64(), t1;
+#define TICK(i)            \
+    t1 = clock64();        \
+    tm[i] += t1 - t0;      \
+    t0 = t1;
     int pos[RPT_MAX];
     bool active[RPT_MAX];
     int pib[RPT_MAX];  // pivot index inside the current block, -1 otherwise
@@ -145,6 +153,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
             }
         }
         // (each thread touches only its own rows of Ab until a winner row is published after a block sync)
+        TICK(5)
 
         // ---- phase B: nsb pivot steps ----
         for (int j = 0; j < nsb; ++j) {
@@ -159,6 +168,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                 }
             }
             const Cand mine = block_argmax(c, red_key, red_pos, red_row, rb);
+            TICK(0)
             // publish my CTA's candidate and its inner-block row (LL words, fire and forget)
             const int par = jg & 1;
             const unsigned epoch = (unsigned)(p.epoch_base + jg + 1);
@@ -186,7 +196,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                 Cand o{((unsigned long long)a.z << 32) | a.x, (int)b.x, (int)b.z};
                 if (better(o, gc)) gc = o;
             }
+            TICK(1)
             const Cand win = block_argmax(gc, red_key, red_pos, red_row, rb);
+            TICK(2)
             // (win.row < 0 cannot happen while jg < nsteps = min(n, v): some row is still active)
             const int wcta = win.row / p.R;
             if (t < nbc) {
@@ -204,11 +216,14 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                 if (cta == 0) p.perm_out[jg] = win.row;
             }
             __syncthreads();
+            TICK(3)
             const double pivot = prow[j];
             const double rinv = pivot != 0.0 ? 1.0 / pivot : 0.0;
+            double lq[RPT_MAX];
 #pragma unroll
             for (int q = 0; q < RPT_MAX; ++q) {
                 const int lr = t + q * PT_THREADS;
+                lq[q] = 0.0;
                 if (!active[q]) continue;
                 if (row_base + lr == win.row) {
                     active[q] = false;
@@ -217,11 +232,24 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                 }
                 if (pos[q] == jg) pos[q] = win.pos;  // the row that sat at position jg moves to the winner's slot
                 if (pivot != 0.0) {
-                    const double l = Ab[j * Rpad + lr] * rinv;
-                    Ab[j * Rpad + lr] = l;
-                    for (int c2 = j + 1; c2 < nbc; ++c2) Ab[c2 * Rpad + lr] -= l * prow[c2];
+                    lq[q] = Ab[j * Rpad + lr] * rinv;
+                    Ab[j * Rpad + lr] = lq[q];
                 }
             }
+            {
+                const double* __restrict__ pr = prow;
+                double* __restrict__ ab = Ab;
+#pragma unroll 4
+                for (int c2 = j + 1; c2 < nbc; ++c2) {
+                    const double pc = pr[c2];
+#pragma unroll
+                    for (int q = 0; q < RPT_MAX; ++q) {
+                        const int lr = t + q * PT_THREADS;
+                        if (active[q] && lr < Rloc) ab[c2 * Rpad + lr] = fma(-lq[q], pc, ab[c2 * Rpad + lr]);
+                    }
+                }
+            }
+            TICK(4)
             // next step's block_argmax syncs before prow / LU11 are overwritten
         }
 
@@ -240,6 +268,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
             }
         }
 
+        TICK(5)
         // ---- phase C: U12 = L11^-1 A12, trailing columns of my rows -= L21 * U12 ----
         const int cstart = jb + nbc;
         const int rem = v - cstart;
@@ -268,6 +297,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                 }
             }
             __syncthreads();
+            TICK(6)
 #pragma unroll 1
             for (int q = 0; q < RPT_MAX; ++q) {
                 const int lr = t + q * PT_THREADS;
@@ -305,10 +335,14 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
 #pragma unroll
         for (int q = 0; q < RPT_MAX; ++q) pib[q] = -1;
         __syncthreads();  // Ab / U12 / LU11 are rewritten by the next block
+        TICK(7)
     }
     // identity tail of perm (n < v): LAPACK leaves perm[i] = i for i >= n (conflux_opt.hpp:150-165)
     if (cta == 0)
         for (int i = p.nsteps + t; i < v; i += PT_THREADS) p.perm_out[i] = i;
+    if (cta == 0 && t == 0 && p.dbg != nullptr)
+        for (int i = 0; i < 8; ++i) p.dbg[i] = tm[i];
+#undef TICK
 }
 
 template <int NB>
@@ -341,12 +375,15 @@ int panel_workspace_create(PanelWorkspace* ws) {
     ws->cta_cap = 0;
     CFLX_CUDA(cudaMalloc(&ws->slot_hdr, sizeof(uint2) * 2 * MAXG * 4));
     CFLX_CUDA(cudaMalloc(&ws->slot_rows, sizeof(uint2) * 2 * MAXG * 64));
+    CFLX_CUDA(cudaMalloc(&ws->dbg, sizeof(long long) * 8));
+    CFLX_CUDA(cudaMemset(ws->dbg, 0, sizeof(long long) * 8));
     CFLX_CUDA(cudaMemset(ws->slot_hdr, 0, sizeof(uint2) * 2 * MAXG * 4));
     CFLX_CUDA(cudaMemset(ws->slot_rows, 0, sizeof(uint2) * 2 * MAXG * 64));
     return CFLX_OK;
 }
 void panel_workspace_destroy(PanelWorkspace* ws) {
     cudaFree(ws->slot_hdr);
+    cudaFree(ws->dbg);
     cudaFree(ws->slot_rows);
     *ws = PanelWorkspace{};
 }
@@ -381,6 +418,7 @@ int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, 
     a.slot_hdr = reinterpret_cast<uint2*>(ws->slot_hdr);
     a.slot_rows = reinterpret_cast<uint2*>(ws->slot_rows);
     a.epoch_base = ws->epoch;
+    a.dbg = ws->dbg;
     ws->epoch += v + 2 + (v & 1);  // keep the base even so slot parity == column parity
     const size_t budget = 222 * 1024;
     int nb = v >= 32 ? 32 : (v >= 16 ? 16 : (v >= 8 ? 8 : 4));

@@ -98,6 +98,9 @@ int cflx_dbg_panel(int n, int v, const double* panel, int* perm_out, double* A00
                    double* ms_out);
 /* X = B * U^-1 (right, upper, non-unit; B n x v) and Y = L^-1 * R (left, lower, unit; R v x n), A00 = L\U packed */
 int cflx_dbg_trsm(int n, int v, const double* A00, const double* B, double* X_out, const double* R, double* Y_out);
+/* cycle counters of CTA 0 of the last cflx_dbg_panel launch: {candidate+argmax, exchange, argmax2, row fetch,
+ * eliminate, load/write-back, U12 gather+solve, rank update} */
+int cflx_dbg_last_panel_cycles(long long* out8);
 /* raw FP64 pipe micro-benchmarks: which = 0 DMMA (mma.sync m8n8k4 f64), 1 DFMA; returns TFLOP/s */
 int cflx_dbg_fp64_peak(int which, double* tflops_out);
 

@@ -15,9 +15,14 @@ for (M, N, K) in [(4096, 4096, 256), (8192, 8192, 256), (16128, 16128, 256), (81
 for (n, v) in [(2048, 256), (16384, 256), (32768, 512), (1024, 512)]:
     P = 5.0 + rng.random((n, v))
     _, _, _, ms = cb.dbg.panel(P, reps=3)
-    print(f"panel n={n} v={v}: {ms:.3f} ms ({ms/v*1e3:.2f} us/column)", flush=True)
+    import ctypes
+    cyc = (ctypes.c_longlong * 8)()
+    cb._lib.lib().cflx_dbg_last_panel_cycles(cyc)
+    names = ["cand+argmax1", "exchange", "argmax2", "rowfetch", "eliminate", "load/wb", "u12", "update"]
+    print(f"panel n={n} v={v}: {ms:.3f} ms ({ms/v*1e3:.2f} us/column)  CTA0 kcycles: " +
+          ", ".join(f"{a}={c/1e3:.0f}" for a, c in zip(names, cyc)), flush=True)
 comm = cb.Comm(1, 0, None, 0)
-cfgs = [(la, ctas, N, v) for (N, v) in [(4096, 256), (8192, 256), (16384, 256)] for (la, ctas) in [(0, 0), (1, 16), (1, 32), (1, 64)]]
+cfgs = [(la, ctas, N, v) for (N, v) in [(8192, 256), (16384, 256)] for (la, ctas) in [(0, 0), (1, 32), (1, 64)]]
 for (la, ctas, N, v) in cfgs:
     os.environ["CFLX_LOOKAHEAD"] = str(la)
     os.environ["CFLX_PANEL_CTAS"] = str(ctas)
