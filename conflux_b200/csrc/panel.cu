@@ -30,7 +30,7 @@ namespace {
 constexpr int PT_THREADS = 128;
 constexpr int PT_WARPS = PT_THREADS / 32;
 constexpr int MAXG = 148;
-constexpr int RPT_MAX = 8;  // rows per thread -> R <= 1024 rows per CTA
+constexpr int RPT_LIMIT = 8;  // rows per thread -> R <= 1024 rows per CTA
 
 struct PanelArgs {
     double* W;
@@ -103,7 +103,7 @@ __device__ __forceinline__ Cand block_argmax(Cand c, unsigned long long* red_key
     return best;
 }
 
-template <int NB>
+template <int NB, int RPT_MAX>
 __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Ab = reinterpret_cast<double*>(smem_raw);  // [NB][Rpad] inner block, column-major per CTA
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
 #pragma unroll
                     for (int q = 0; q < RPT_MAX; ++q) {
                         const int lr = t + q * PT_THREADS;
-                        if (active[q] && lr < Rloc) ab[c2 * Rpad + lr] = fma(-lq[q], pc, ab[c2 * Rpad + lr]);
+                        if (active[q]) ab[c2 * Rpad + lr] = fma(-lq[q], pc, ab[c2 * Rpad + lr]);
                     }
                 }
             }
@@ -351,18 +351,26 @@ size_t panel_smem_bytes(int Rpad, int v) {
            2 * PT_WARPS * (sizeof(unsigned long long) + 2 * sizeof(int)) + NB * sizeof(int) + 64;
 }
 
-template <int NB>
-int launch_nb(PanelArgs& a, cudaStream_t stream) {
+template <int NB, int RPT>
+int launch_nb_rpt(PanelArgs& a, cudaStream_t stream) {
     const size_t smem = panel_smem_bytes<NB>(a.Rpad, a.v);
     static size_t configured = 0;
     if (smem > configured) {
-        CFLX_CUDA(cudaFuncSetAttribute(panel_getrf_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CFLX_CUDA(cudaFuncSetAttribute(panel_getrf_kernel<NB, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     void* params[] = {&a};
-    CFLX_CUDA(cudaLaunchCooperativeKernel((void*)panel_getrf_kernel<NB>, dim3(a.G), dim3(PT_THREADS), params, smem,
+    CFLX_CUDA(cudaLaunchCooperativeKernel((void*)panel_getrf_kernel<NB, RPT>, dim3(a.G), dim3(PT_THREADS), params, smem,
                                           stream));
     return CFLX_OK;
+}
+template <int NB>
+int launch_nb(PanelArgs& a, cudaStream_t stream) {
+    const int rpt = (a.R + PT_THREADS - 1) / PT_THREADS;
+    if (rpt <= 1) return launch_nb_rpt<NB, 1>(a, stream);
+    if (rpt <= 2) return launch_nb_rpt<NB, 2>(a, stream);
+    if (rpt <= 4) return launch_nb_rpt<NB, 4>(a, stream);
+    return launch_nb_rpt<NB, 8>(a, stream);
 }
 }  // namespace
 
@@ -406,8 +414,8 @@ int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, 
     int R = (n + G - 1) / G;
     R = (int)round_up(R > 0 ? R : 1, 32);
     G = n > 0 ? (n + R - 1) / R : 1;
-    if (R > RPT_MAX * PT_THREADS) {
-        set_last_error("panel_getrf: n=%d rows exceed the %d-row capacity", n, ws->max_ctas * RPT_MAX * PT_THREADS);
+    if (R > RPT_LIMIT * PT_THREADS) {
+        set_last_error("panel_getrf: n=%d rows exceed the %d-row capacity", n, ws->max_ctas * RPT_LIMIT * PT_THREADS);
         return CFLX_ERR_UNSUPPORTED;
     }
     a.R = R;
