@@ -29,6 +29,23 @@ void set_last_error(const char* fmt, ...);
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// cudaFuncSetAttribute is per DEVICE: ranks may be threads of one process driving different GPUs, so the
+// "already configured" bookkeeping is kept per device ordinal (values only grow; a benign race re-applies it).
+struct PerDeviceMax {
+    size_t v[64] = {0};
+    // returns true when `want` exceeds what was configured on the current device (and records it)
+    bool raise(size_t want) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        if (want > v[dev]) {
+            v[dev] = want;
+            return true;
+        }
+        return false;
+    }
+};
+
 #ifdef __CUDACC__
 // ---- mbarrier / bulk-copy (TMA engine, UBLKCP in SASS) PTX wrappers --------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -136,11 +136,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_kernel(GemmArgs g) {
 }  // namespace
 
 int gemm_tn_setup() {
-    static bool done = false;
-    if (!done) {
+    static PerDeviceMax cfg;
+    if (cfg.raise(SMEM_BYTES))
         CFLX_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        done = true;
-    }
     return CFLX_OK;
 }
 

@@ -354,11 +354,9 @@ size_t panel_smem_bytes(int Rpad, int v) {
 template <int NB, int RPT>
 int launch_nb_rpt(PanelArgs& a, cudaStream_t stream) {
     const size_t smem = panel_smem_bytes<NB>(a.Rpad, a.v);
-    static size_t configured = 0;
-    if (smem > configured) {
+    static PerDeviceMax cfg;
+    if (cfg.raise(smem))
         CFLX_CUDA(cudaFuncSetAttribute(panel_getrf_kernel<NB, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     void* params[] = {&a};
     CFLX_CUDA(cudaLaunchCooperativeKernel((void*)panel_getrf_kernel<NB, RPT>, dim3(a.G), dim3(PT_THREADS), params, smem,
                                           stream));

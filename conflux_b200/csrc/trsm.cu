@@ -53,11 +53,9 @@ __global__ void diag_inverse_kernel(const double* __restrict__ A00, int v, int n
 int launch_diag_inverses(const double* A00, int v, int nb, double* Uinv, double* LinvT, cudaStream_t stream) {
     const int nblk = v / nb;
     const size_t smem = 2 * (size_t)nb * (nb + 1) * sizeof(double);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static PerDeviceMax cfg;
+    if (smem > 48 * 1024 && cfg.raise(smem))
         CFLX_CUDA(cudaFuncSetAttribute(diag_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     const int threads = ((nb + 31) / 32) * 32;
     diag_inverse_kernel<<<dim3(nblk, 2), threads < 64 ? 64 : threads, smem, stream>>>(A00, v, nb, Uinv, LinvT);
     CFLX_CUDA(cudaGetLastError());

@@ -29,6 +29,11 @@ def run_ranks(P, fn):
                 comm.close()
         except BaseException as e:  # noqa: BLE001
             err[r] = e
+            import sys
+            import traceback
+            sys.stderr.write(f"[rank {r}] failed: {e!r}\n")
+            traceback.print_exc()
+            sys.stderr.flush()
 
     th = [threading.Thread(target=body, args=(r,)) for r in range(P)]
     for t in th:
