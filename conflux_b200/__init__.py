@@ -200,6 +200,13 @@ class dbg:
         return X, Y
 
     @staticmethod
+    def fp64_peak_ex(which):
+        """(burst, sustained) TFLOP/s of the DMMA (0) / DFMA (1) pipe."""
+        a, b = ctypes.c_double(), ctypes.c_double()
+        check(lib().cflx_dbg_fp64_peak_ex(int(which), ctypes.byref(a), ctypes.byref(b)), "dbg_fp64_peak_ex")
+        return a.value, b.value
+
+    @staticmethod
     def fp64_peak(which):
         tf = ctypes.c_double()
         check(lib().cflx_dbg_fp64_peak(int(which), ctypes.byref(tf)), "dbg_fp64_peak")

@@ -103,6 +103,8 @@ int cflx_dbg_trsm(int n, int v, const double* A00, const double* B, double* X_ou
 int cflx_dbg_last_panel_cycles(long long* out8);
 /* raw FP64 pipe micro-benchmarks: which = 0 DMMA (mma.sync m8n8k4 f64), 1 DFMA; returns TFLOP/s */
 int cflx_dbg_fp64_peak(int which, double* tflops_out);
+/* same probe: burst (best of ~2 ms launches) and sustained (one ~0.5 s launch, power-capped) TFLOP/s */
+int cflx_dbg_fp64_peak_ex(int which, double* burst_out, double* sustained_out);
 
 #ifdef __cplusplus
 }
