@@ -176,9 +176,9 @@ def main():
     comm = cb.Comm.from_torch_distributed(device=local_rank) if world > 1 else cb.Comm(1, 0, None, local_rank)
     gv = cb.lu_params(N, N, v, Px, Py, Pz, comm)
     # pinned host staging for the end-to-end arm
-    host = torch.empty((gv.Ml, gv.Nl), dtype=torch.float64, pin_memory=True)
-    host.numpy()[...] = gv.data
-    gv.data = host.numpy()
+    host = cb.pinned_empty((gv.Ml, gv.Nl))        # cudaHostAlloc through the library (torch never touches CUDA here)
+    host[...] = gv.data
+    gv.data = host
     perm = np.zeros(gv.M, dtype=np.int32)
     flops = (2.0 / 3.0) * float(gv.N) ** 3
 

@@ -15,7 +15,7 @@ import numpy as np
 
 from ._lib import ConfluxError, LIB_PATH, SYMBOLS, check, lib
 
-__all__ = ["Comm", "lu_params", "LU_rep", "auto_grid", "lu_dims", "init_matrix_host", "ConfluxError", "dbg"]
+__all__ = ["pinned_empty", "pinned_free", "Comm", "lu_params", "LU_rep", "auto_grid", "lu_dims", "init_matrix_host", "ConfluxError", "dbg"]
 
 
 def auto_grid(M, N, P):
@@ -40,6 +40,26 @@ def init_matrix_host(M, N, v, Px, Py, Pz, rank, seed=42, out=None):
     check(lib().cflx_init_matrix_host(int(M), int(N), int(v), int(Px), int(Py), int(Pz), int(rank), int(seed),
                                       out.ctypes.data), "init_matrix_host")
     return out
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array backed by page-locked host memory (cudaHostAlloc) -- staging for LU_rep's host->device copy."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = ctypes.c_void_p()
+    check(lib().cflx_host_alloc(n, ctypes.byref(p)), "host_alloc")
+    buf = (ctypes.c_char * n).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    _PINNED[arr.ctypes.data] = p
+    return arr
+
+
+_PINNED = {}
+
+
+def pinned_free(arr):
+    p = _PINNED.pop(arr.ctypes.data, None)
+    if p is not None:
+        lib().cflx_host_free(p)
 
 
 class Comm:

@@ -20,7 +20,7 @@ class ConfluxError(RuntimeError):
 # every exported symbol of include/conflux_b200.h (checked by tests/test_abi.py)
 SYMBOLS = [
     "cflx_last_error", "cflx_version", "cflx_device_count", "cflx_get_unique_id", "cflx_comm_create",
-    "cflx_comm_barrier", "cflx_comm_destroy", "cflx_auto_grid", "cflx_lu_dims", "cflx_init_matrix_host",
+    "cflx_comm_barrier", "cflx_comm_destroy", "cflx_host_alloc", "cflx_host_free", "cflx_auto_grid", "cflx_lu_dims", "cflx_init_matrix_host",
     "cflx_lu_create", "cflx_lu_info", "cflx_lu_set_local", "cflx_lu_factor", "cflx_lu_get_factors",
     "cflx_lu_get_permutation", "cflx_lu_launch_count", "cflx_lu_set_profiling", "cflx_lu_phase_ms",
     "cflx_lu_set_kernel_timing", "cflx_lu_trailing_stats", "cflx_lu_destroy", "cflx_dbg_gemm_tn", "cflx_dbg_panel", "cflx_dbg_trsm", "cflx_dbg_last_panel_cycles", "cflx_dbg_fp64_peak", "cflx_dbg_fp64_peak_ex",
@@ -45,6 +45,8 @@ def lib():
         L.cflx_comm_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                        ctypes.POINTER(ctypes.c_void_p)]
         L.cflx_lu_create.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.POINTER(ctypes.c_void_p)]
+        L.cflx_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+        L.cflx_host_free.argtypes = [ctypes.c_void_p]
         L.cflx_lu_info.argtypes = [ctypes.c_void_p, c_int_p]
         L.cflx_lu_set_local.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.cflx_lu_factor.argtypes = [ctypes.c_void_p, c_double_p]

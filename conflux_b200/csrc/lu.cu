@@ -873,6 +873,22 @@ int cflx_lu_get_factors(cflx_lu* lu, double* C_host, int* perm_out) {
     return CFLX_OK;
 }
 
+int cflx_host_alloc(size_t bytes, void** out) {
+    if (!out) return CFLX_ERR_ARG;
+    int n = 0;
+    cflx_device_count(&n);
+    if (n == 0) {
+        set_last_error("no CUDA device visible: conflux_b200 has no CPU fallback");
+        return CFLX_ERR_NO_DEVICE;
+    }
+    CFLX_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return CFLX_OK;
+}
+int cflx_host_free(void* p) {
+    if (p) CFLX_CUDA(cudaFreeHost(p));
+    return CFLX_OK;
+}
+
 int cflx_lu_launch_count(cflx_lu* lu, int64_t* count_out, int reset) {
     if (!lu || !count_out) return CFLX_ERR_ARG;
     *count_out = lu->launches;

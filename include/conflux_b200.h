@@ -20,6 +20,7 @@
 #ifndef CONFLUX_B200_H
 #define CONFLUX_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -52,6 +53,10 @@ int cflx_get_unique_id(void* id_out /* CFLX_UNIQUE_ID_BYTES */);
 int cflx_comm_create(int world_size, int world_rank, const void* unique_id, int device, cflx_comm** out);
 int cflx_comm_barrier(cflx_comm*); /* COLLECTIVE: device-side barrier + host synchronisation */
 void cflx_comm_destroy(cflx_comm*);
+
+/* page-locked host staging buffers for cflx_lu_set_local (cudaHostAlloc / cudaFreeHost) */
+int cflx_host_alloc(size_t bytes, void** out);
+int cflx_host_free(void* p);
 
 /* ---- sizes (pure host arithmetic, no device needed) ---------------------------------------------------- */
 /* lu_params::get_p_grid for a square matrix: P = 1 -> 1x1x1, 2 -> 1x1x2, 4 -> 2x2x1, 8 -> 2x2x2, ... */
