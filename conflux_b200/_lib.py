@@ -27,6 +27,22 @@ SYMBOLS = [
 ]
 
 
+def _preload_nccl():
+    """libconflux_b200.so needs `libnccl.so.2`.  PyTorch bundles a newer NCCL under the same soname; if ours were
+    loaded first a later `import torch` would bind to the older system library and fail to resolve its symbols, so
+    the bundled one (when present) is loaded first and shared by both."""
+    import sys
+    for d in sys.path:
+        cand = os.path.join(d, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                ctypes.CDLL(cand, mode=ctypes.RTLD_GLOBAL)
+                return cand
+            except OSError:
+                pass
+    return None
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -34,6 +50,7 @@ def lib():
             raise ConfluxError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(conflux_b200 has no CPU fallback)")
+        _preload_nccl()
         L = ctypes.CDLL(LIB_PATH)
         L.cflx_last_error.restype = ctypes.c_char_p
         L.cflx_version.restype = ctypes.c_char_p

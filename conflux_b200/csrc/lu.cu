@@ -750,9 +750,6 @@ int cflx_lu_factor(cflx_lu* lu, double* ms_out) {
     lu->gemm_ms = 0;
     if (lu->time_gemm && (int)lu->ev.size() < 4 * lu->Nt) {
         for (auto& e : lu->ev) cudaEventDestroy(e);
-    if (lu->side) cudaStreamDestroy(lu->side);
-    if (lu->ev_fork) cudaEventDestroy(lu->ev_fork);
-    if (lu->ev_join) cudaEventDestroy(lu->ev_join);
         lu->ev.assign(4 * lu->Nt, nullptr);
         for (auto& e : lu->ev) CFLX_CUDA(cudaEventCreate(&e));
     }
