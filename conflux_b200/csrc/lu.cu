@@ -74,11 +74,9 @@ int butterfly_pair(int pi, int r, int Px) {  // conflux_opt.cpp:59-72
     }
     return src;
 }
-int pick_nb(int v) {
-    if (v % 64 == 0) return 64;
-    if (v <= 128) return v;
-    if (v % 32 == 0) return 32;
-    if (v % 16 == 0) return 16;
+int pick_nb(int v) {  // block size of the diagonal inverses / TRSM sweeps (template instances: 64, 32, 16, 8, 4)
+    for (int nb : {64, 32, 16, 8, 4})
+        if (v % nb == 0) return nb;
     return 0;
 }
 }  // namespace
@@ -413,16 +411,22 @@ int finish_step(cflx_lu* lu, int k, int& fnpr) {
         PhaseTimer t(lu, PH_REDUCE);
         CFLX_NCCL(ncclBroadcast(lu->LT, lu->LT, (size_t)v * ld2, ncclDouble, pjk * Pz, lu->jk_comm.c, s));
     }
+    // The U solve is split in two column windows: the first v columns (= the next panel) are solved before the
+    // look-ahead fork, the rest after it, off the pivot search's critical path (single-rank grids only: with more
+    // ranks the U panel is broadcast whole).
+    const bool split_u = (lu->P == 1) && (k + 1 < lu->Nt) && ncols > v;
+    const int ncols_a = split_u ? v : ncols;
     if (on_row && layer0 && ncols > 0) {
         PhaseTimer t(lu, PH_TRSM);
-        CFLX_TRY(trsm_left_lower_unit(lu->A00T, lu->LinvT, v, lu->nb, lu->A01raw, lu->U, ldu, ncols, s));
+        CFLX_TRY(trsm_left_lower_unit(lu->A00T, lu->LinvT, v, lu->nb, lu->A01raw, lu->U, ldu, ncols_a, s));
         lu->launches += 2 * (v / lu->nb) - 1;
     }
     if (Px * Pz > 1 && ncols > 0) {  // U panel to every (pi', pk') of my grid column   conflux_opt.hpp:1567-1593
         PhaseTimer t(lu, PH_REDUCE);
         CFLX_NCCL(ncclBroadcast(lu->U, lu->U, (size_t)v * ldu, ncclDouble, pik * Pz, lu->ik_comm.c, s));
     }
-    if (layer0) {  // factor storage: my promoted rows receive their U part and diagonal block   :1721-1754
+    auto store_factors = [&]() -> int {  // my promoted rows receive their U part and diagonal block   :1721-1754
+        if (!layer0) return CFLX_OK;
         PhaseTimer t(lu, PH_STORE);
         if (ncols > 0) {
             CFLX_TRY(launch_store_u_rows(lu->A11, Nl, fnpr_old, lu->plan, lu->U, ldu, c0, ncols, v, s));
@@ -432,7 +436,9 @@ int finish_step(cflx_lu* lu, int k, int& fnpr) {
             CFLX_TRY(launch_store_diag(lu->A11, Nl, fnpr_old, lu->plan, lu->A00, loff, v, s));
             lu->launches++;
         }
-    }
+        return CFLX_OK;
+    };
+    if (!split_u) CFLX_TRY(store_factors());
     // ---- step 6: trailing update on every rank and layer                    conflux_opt.hpp:1628-1632
     // Look-ahead: the rank that owns panel k+1 updates those v columns first (they are its first live block), forks
     // the pivot search of iteration k+1 onto the side stream, and only then updates the remaining columns.
@@ -448,6 +454,12 @@ int finish_step(cflx_lu* lu, int k, int& fnpr) {
         }
         CFLX_TRY(panel_phase(lu, k + 1, fnpr, sp));
         if (side) CFLX_CUDA(cudaEventRecord(lu->ev_join, sp));
+        if (split_u) {
+            PhaseTimer t(lu, PH_TRSM);
+            CFLX_TRY(trsm_left_lower_unit(lu->A00T, lu->LinvT, v, lu->nb, lu->A01raw + v, lu->U + v, ldu, ncols - v, s));
+            lu->launches += 2 * (v / lu->nb) - 1;
+        }
+        if (split_u) CFLX_TRY(store_factors());
         CFLX_TRY(trailing_gemm(lu, k, 1, fnpr, n_act, c0 + w, ncols - w, ld2, ldu, w, s));
         if (side) CFLX_CUDA(cudaStreamWaitEvent(s, lu->ev_join, 0));
     } else {
@@ -621,7 +633,7 @@ int cflx_lu_create(cflx_comm* c, int M, int N, int v, int Px, int Py, int Pz, cf
         return CFLX_ERR_ARG;
     }
     if (v % 4 != 0 || v % Pz != 0 || (v / Pz) % 4 != 0 || pick_nb(v) == 0) {
-        set_last_error("tile size v=%d unsupported: need v %% 4 == 0, (v / Pz) %% 4 == 0 and v <= 128 or v %% 16 == 0", v);
+        set_last_error("tile size v=%d unsupported: need v %% 4 == 0 and (v / Pz) %% 4 == 0", v);
         return CFLX_ERR_UNSUPPORTED;
     }
     int d[8];

@@ -12,54 +12,76 @@
 
 namespace cflx {
 namespace {
-// grid = (nblk, 2): y == 0 -> Uinv[j] = inv(U_jj) row-major; y == 1 -> LinvT[j] = inv(L_jj)^T row-major
-__global__ void diag_inverse_kernel(const double* __restrict__ A00, int v, int nb, double* __restrict__ Uinv,
-                                    double* __restrict__ LinvT) {
-    extern __shared__ double sm[];
-    double* S = sm;                  // [nb][nb+1] the diagonal block
-    double* X = sm + nb * (nb + 1);  // [nb][nb+1] result (column c owned by thread c)
+// grid = (nblk, 2): y == 0 -> Uinv[j] = inv(U_jj) row-major; y == 1 -> LinvT[j] = inv(L_jj)^T row-major.
+// Thread c owns column c of the inverse and keeps it in registers; the triangular block is read from shared memory
+// with warp-uniform (broadcast) addresses, so the whole substitution is NB^2/2 register FMAs per thread.
+template <int NB>
+__global__ void __launch_bounds__(NB < 32 ? 32 : NB) diag_inverse_kernel(const double* __restrict__ A00, int v,
+                                                                         double* __restrict__ Uinv,
+                                                                         double* __restrict__ LinvT) {
+    __shared__ double S[NB][NB + 1];
     const int j = blockIdx.x, c = threadIdx.x;
-    const double* blk = A00 + (size_t)(j * nb) * v + j * nb;
-    for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) S[(e / nb) * (nb + 1) + e % nb] = blk[(size_t)(e / nb) * v + e % nb];
+    const double* blk = A00 + (size_t)(j * NB) * v + j * NB;
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) S[e / NB][e % NB] = blk[(size_t)(e / NB) * v + e % NB];
     __syncthreads();
-    if (c < nb) {
-        if (blockIdx.y == 0) {  // U X = I, column c by back substitution
-            for (int r = nb - 1; r > c; --r) X[r * (nb + 1) + c] = 0.0;
-            X[c * (nb + 1) + c] = 1.0 / S[c * (nb + 1) + c];
-            for (int r = c - 1; r >= 0; --r) {
-                double s = 0.0;
-                for (int t = r + 1; t <= c; ++t) s += S[r * (nb + 1) + t] * X[t * (nb + 1) + c];
-                X[r * (nb + 1) + c] = -s / S[r * (nb + 1) + r];
+    if (c >= NB) return;
+    double x[NB];
+    double* out = (blockIdx.y == 0 ? Uinv : LinvT) + (size_t)j * NB * NB;
+    if (blockIdx.y == 0) {  // U X = I: x[c] = 1/U[c][c]; x[r] = -(sum_{t=r+1..c} U[r][t] x[t]) / U[r][r], r < c
+#pragma unroll
+        for (int r = NB - 1; r >= 0; --r) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int t = r + 1; t < NB; ++t) {
+                const double u = S[r][t];
+                if (t <= c) {
+                    if (t & 1) s1 = fma(u, x[t], s1);
+                    else s0 = fma(u, x[t], s0);
+                }
             }
-        } else {  // L Y = I (unit diagonal), column c by forward substitution
-            for (int r = 0; r < c; ++r) X[r * (nb + 1) + c] = 0.0;
-            X[c * (nb + 1) + c] = 1.0;
-            for (int r = c + 1; r < nb; ++r) {
-                double s = 0.0;
-                for (int t = c; t < r; ++t) s += S[r * (nb + 1) + t] * X[t * (nb + 1) + c];
-                X[r * (nb + 1) + c] = -s;
-            }
+            const double d = S[r][r];
+            x[r] = r > c ? 0.0 : (r == c ? 1.0 / d : -(s0 + s1) / d);
         }
+#pragma unroll
+        for (int r = 0; r < NB; ++r) out[(size_t)r * NB + c] = x[r];  // Uinv[r][c]
+    } else {  // L Y = I (unit diagonal): y[c] = 1; y[r] = -sum_{t=c..r-1} L[r][t] y[t], r > c
+#pragma unroll
+        for (int r = 0; r < NB; ++r) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int t = 0; t < r; ++t) {
+                const double l = S[r][t];
+                if (t >= c) {
+                    if (t & 1) s1 = fma(l, x[t], s1);
+                    else s0 = fma(l, x[t], s0);
+                }
+            }
+            x[r] = r < c ? 0.0 : (r == c ? 1.0 : -(s0 + s1));
+        }
+#pragma unroll
+        for (int r = 0; r < NB; ++r) out[(size_t)c * NB + r] = x[r];  // LinvT[c][r] = Linv[r][c]
     }
-    __syncthreads();
-    double* out = (blockIdx.y == 0 ? Uinv : LinvT) + (size_t)j * nb * nb;
-    for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
-        const int r = e / nb, cc = e % nb;
-        out[e] = blockIdx.y == 0 ? X[r * (nb + 1) + cc] : X[cc * (nb + 1) + r];
-    }
+}
+
+template <int NB>
+int launch_diag_nb(const double* A00, int v, double* Uinv, double* LinvT, cudaStream_t stream) {
+    diag_inverse_kernel<NB><<<dim3(v / NB, 2), NB < 32 ? 32 : NB, 0, stream>>>(A00, v, Uinv, LinvT);
+    CFLX_CUDA(cudaGetLastError());
+    return CFLX_OK;
 }
 }  // namespace
 
 int launch_diag_inverses(const double* A00, int v, int nb, double* Uinv, double* LinvT, cudaStream_t stream) {
-    const int nblk = v / nb;
-    const size_t smem = 2 * (size_t)nb * (nb + 1) * sizeof(double);
-    static PerDeviceMax cfg;
-    if (smem > 48 * 1024 && cfg.raise(smem))
-        CFLX_CUDA(cudaFuncSetAttribute(diag_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int threads = ((nb + 31) / 32) * 32;
-    diag_inverse_kernel<<<dim3(nblk, 2), threads < 64 ? 64 : threads, smem, stream>>>(A00, v, nb, Uinv, LinvT);
-    CFLX_CUDA(cudaGetLastError());
-    return CFLX_OK;
+    switch (nb) {
+        case 64: return launch_diag_nb<64>(A00, v, Uinv, LinvT, stream);
+        case 32: return launch_diag_nb<32>(A00, v, Uinv, LinvT, stream);
+        case 16: return launch_diag_nb<16>(A00, v, Uinv, LinvT, stream);
+        case 8: return launch_diag_nb<8>(A00, v, Uinv, LinvT, stream);
+        case 4: return launch_diag_nb<4>(A00, v, Uinv, LinvT, stream);
+        default:
+            set_last_error("diag_inverses: unsupported block size %d", nb);
+            return CFLX_ERR_UNSUPPORTED;
+    }
 }
 
 // X * U00 = P  <=>  U00^T X^T = P^T.  PT/LT are the transposed panels [v][ld]; sweep over block rows j:
@@ -96,6 +118,7 @@ int trsm_right_upper_T(const double* A00, const double* Uinv, int v, int nb, dou
 // L00 * X = R (unit lower).  R/U are [v][ld]:  U_j = inv(L_jj) * R_j ;  R_i -= L_ij * U_j  (i > j)
 int trsm_left_lower_unit(const double* A00T, const double* LinvT, int v, int nb, double* R, double* U, int64_t ld, int n,
                          cudaStream_t stream) {
+    // (callers solve a column window by offsetting R and U: the columns are independent right-hand sides)
     if (n <= 0) return CFLX_OK;
     const int nblk = v / nb;
     for (int j = 0; j < nblk; ++j) {

@@ -8,7 +8,7 @@ import conflux_b200 as cb
 
 print("FP64 pipe: DMMA %.2f TFLOP/s, DFMA %.2f TFLOP/s" % (cb.dbg.fp64_peak(0), cb.dbg.fp64_peak(1)), flush=True)
 rng = np.random.default_rng(0)
-for (M, N, K) in [(4096, 4096, 256), (8192, 8192, 256), (16128, 16128, 256), (8192, 8192, 512), (8192, 8192, 128)]:
+for (M, N, K) in [(16128, 16128, 256), (8192, 8192, 512)]:
     AT, B = rng.standard_normal((K, M)), rng.standard_normal((K, N))
     _, ms = cb.dbg.gemm_tn(AT, B, None, -1.0, 1.0, reps=5)
     print(f"gemm_tn M={M} N={N} K={K}: {ms:.3f} ms  {2.0*M*N*K/ms/1e9:.2f} TFLOP/s", flush=True)
@@ -22,7 +22,7 @@ for (n, v) in [(2048, 256), (16384, 256), (32768, 512), (1024, 512)]:
     print(f"panel n={n} v={v}: {ms:.3f} ms ({ms/v*1e3:.2f} us/column)  CTA0 kcycles: " +
           ", ".join(f"{a}={c/1e3:.0f}" for a, c in zip(names, cyc)), flush=True)
 comm = cb.Comm(1, 0, None, 0)
-cfgs = [(la, ctas, N, v) for (N, v) in [(8192, 256), (16384, 256)] for (la, ctas) in [(0, 0), (1, 32), (1, 64)]]
+cfgs = [(la, ctas, N, v) for (N, v) in [(8192, 256), (16384, 256)] for (la, ctas) in [(1, 24), (1, 32), (1, 48)]]
 for (la, ctas, N, v) in cfgs:
     os.environ["CFLX_LOOKAHEAD"] = str(la)
     os.environ["CFLX_PANEL_CTAS"] = str(ctas)
