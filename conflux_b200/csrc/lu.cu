@@ -226,6 +226,10 @@ int panel_phase(cflx_lu* lu, int k, int fnpr, cudaStream_t s) {
     const int pi = lu->pi, pj = lu->pj, pk = lu->pk;
     const int loff = (k / Py) * v, pjk = k % Py;
     if (pj != pjk) return CFLX_OK;
+    // A00 / A00T are double-buffered by step parity: the look-ahead search of step k+1 must not overwrite the block
+    // that the U solve and the factor stores of step k are still reading on the main stream
+    double* A00 = lu->A00 + (size_t)(k & 1) * v * v;
+    double* A00T = lu->A00T + (size_t)(k & 1) * v * v;
     const int n_old = Ml - fnpr;
     const int64_t ldk = std::max<int64_t>(2, round_up(n_old, 2));
     int nR = 0;
@@ -246,8 +250,8 @@ int panel_phase(cflx_lu* lu, int k, int fnpr, cudaStream_t s) {
         CFLX_CUDA(cudaMemcpyAsync(lu->W, lu->PT, (size_t)v * ldk * sizeof(double), cudaMemcpyDeviceToDevice, s));
         int nb_used = 0;
         if (nR == 0) {  // the local search already is the tournament: A00 comes from it
-            CFLX_TRY(launch_panel_getrf_a00(lu->W, ldk, n_old, v, lu->perm, lu->A00, &nb_used, &lu->pws, s));
-            CFLX_TRY(launch_gather_a00(lu->W, ldk, lu->perm, v, nb_used, lu->A00, lu->A00T, s));
+            CFLX_TRY(launch_panel_getrf_a00(lu->W, ldk, n_old, v, lu->perm, A00, &nb_used, &lu->pws, s));
+            CFLX_TRY(launch_gather_a00(lu->W, ldk, lu->perm, v, nb_used, A00, A00T, s));
             lu->launches += 2;
         } else {
             CFLX_TRY(launch_panel_getrf(lu->W, ldk, n_old, v, lu->perm, &lu->pws, s));
@@ -269,8 +273,8 @@ int panel_phase(cflx_lu* lu, int k, int fnpr, cudaStream_t s) {
         const bool last = (r == nR - 1);
         int nb_used = 0;
         if (last) {
-            CFLX_TRY(launch_panel_getrf_a00(lu->W2, 2 * v, 2 * v, v, lu->perm, lu->A00, &nb_used, &lu->pws, s));
-            CFLX_TRY(launch_gather_a00(lu->W2, 2 * v, lu->perm, v, nb_used, lu->A00, lu->A00T, s));
+            CFLX_TRY(launch_panel_getrf_a00(lu->W2, 2 * v, 2 * v, v, lu->perm, A00, &nb_used, &lu->pws, s));
+            CFLX_TRY(launch_gather_a00(lu->W2, 2 * v, lu->perm, v, nb_used, A00, A00T, s));
             lu->launches++;
             my_half = 0;
         } else {
@@ -328,17 +332,19 @@ int finish_step(cflx_lu* lu, int k, int& fnpr) {
     const int64_t ldk = std::max<int64_t>(2, round_up(n_old, 2));
     int nR = 0;
     while ((1 << nR) < Px) ++nR;
+    double* A00 = lu->A00 + (size_t)(k & 1) * v * v;
+    double* A00T = lu->A00T + (size_t)(k & 1) * v * v;
     // ---- A00 + pivot ids to everybody (one broadcast)                     conflux_opt.hpp:818-850,872
     {
         PhaseTimer t(lu, PH_TOURN);
         if (lu->P > 1) {
             const int root = (pik * Py + pjk) * Pz;  // rank of (k % Px, k % Py, 0)
             if (lu->rank == root) {
-                CFLX_TRY(launch_pack_bcast(lu->A00, lu->tagsH, v, lu->bcast, s));
+                CFLX_TRY(launch_pack_bcast(A00, lu->tagsH, v, lu->bcast, s));
                 lu->launches++;
             }
             CFLX_NCCL(ncclBroadcast(lu->bcast, lu->bcast, (size_t)v * v + v, ncclDouble, root, lu->comm->world, s));
-            CFLX_TRY(launch_unpack_bcast(lu->bcast, v, lu->A00, lu->A00T, lu->gpivots, s));
+            CFLX_TRY(launch_unpack_bcast(lu->bcast, v, A00, A00T, lu->gpivots, s));
             lu->launches++;
         } else {
             CFLX_CUDA(cudaMemcpyAsync(lu->gpivots, lu->tagsH, v * sizeof(int), cudaMemcpyDeviceToDevice, s));
@@ -394,13 +400,13 @@ int finish_step(cflx_lu* lu, int k, int& fnpr) {
     // ---- steps 4/5: the two triangular solves                              conflux_opt.hpp:1329-1359,1522-1551
     if (layer0 && ((on_col && !fused_l) || on_row)) {
         PhaseTimer t(lu, PH_TRSM);
-        CFLX_TRY(launch_diag_inverses(lu->A00, v, lu->nb, lu->Uinv, lu->LinvT, s));
+        CFLX_TRY(launch_diag_inverses(A00, v, lu->nb, lu->Uinv, lu->LinvT, s));
         lu->launches++;
     }
     if (on_col && layer0 && n_act > 0) {
         if (!fused_l) {
             PhaseTimer t(lu, PH_TRSM);
-            CFLX_TRY(trsm_right_upper_T(lu->A00, lu->Uinv, v, lu->nb, lu->PT2, lu->LT, ld2, n_act, s));
+            CFLX_TRY(trsm_right_upper_T(A00, lu->Uinv, v, lu->nb, lu->PT2, lu->LT, ld2, n_act, s));
             lu->launches += 2 * (v / lu->nb) - 1;
         }
         PhaseTimer t(lu, PH_STORE);
@@ -418,7 +424,7 @@ int finish_step(cflx_lu* lu, int k, int& fnpr) {
     const int ncols_a = split_u ? v : ncols;
     if (on_row && layer0 && ncols > 0) {
         PhaseTimer t(lu, PH_TRSM);
-        CFLX_TRY(trsm_left_lower_unit(lu->A00T, lu->LinvT, v, lu->nb, lu->A01raw, lu->U, ldu, ncols_a, s));
+        CFLX_TRY(trsm_left_lower_unit(A00T, lu->LinvT, v, lu->nb, lu->A01raw, lu->U, ldu, ncols_a, s));
         lu->launches += 2 * (v / lu->nb) - 1;
     }
     if (Px * Pz > 1 && ncols > 0) {  // U panel to every (pi', pk') of my grid column   conflux_opt.hpp:1567-1593
@@ -433,7 +439,7 @@ int finish_step(cflx_lu* lu, int k, int& fnpr) {
             lu->launches++;
         }
         if (on_col) {
-            CFLX_TRY(launch_store_diag(lu->A11, Nl, fnpr_old, lu->plan, lu->A00, loff, v, s));
+            CFLX_TRY(launch_store_diag(lu->A11, Nl, fnpr_old, lu->plan, A00, loff, v, s));
             lu->launches++;
         }
         return CFLX_OK;
@@ -456,7 +462,7 @@ int finish_step(cflx_lu* lu, int k, int& fnpr) {
         if (side) CFLX_CUDA(cudaEventRecord(lu->ev_join, sp));
         if (split_u) {
             PhaseTimer t(lu, PH_TRSM);
-            CFLX_TRY(trsm_left_lower_unit(lu->A00T, lu->LinvT, v, lu->nb, lu->A01raw + v, lu->U + v, ldu, ncols - v, s));
+            CFLX_TRY(trsm_left_lower_unit(A00T, lu->LinvT, v, lu->nb, lu->A01raw + v, lu->U + v, ldu, ncols - v, s));
             lu->launches += 2 * (v / lu->nb) - 1;
         }
         if (split_u) CFLX_TRY(store_factors());
@@ -671,7 +677,7 @@ int cflx_lu_create(cflx_comm* c, int M, int N, int v, int Px, int Py, int Pz, cf
     ALLOC(lu->A0, loc); ALLOC(lu->A11, loc);
     ALLOC(lu->PT, pan); ALLOC(lu->PT2, pan); ALLOC(lu->W, pan); ALLOC(lu->LT, pan);
     ALLOC(lu->A01raw, upan); ALLOC(lu->U, upan); ALLOC(lu->tmp, (size_t)v * lu->Nl);
-    ALLOC(lu->A00, vv); ALLOC(lu->A00T, vv); ALLOC(lu->Uinv, vv); ALLOC(lu->LinvT, vv);
+    ALLOC(lu->A00, 2 * vv); ALLOC(lu->A00T, 2 * vv); ALLOC(lu->Uinv, vv); ALLOC(lu->LinvT, vv);
     ALLOC(lu->candH, 2 * vv); ALLOC(lu->S, 2 * vv); ALLOC(lu->W2, 2 * vv); ALLOC(lu->bcast, vv + v);
     ALLOC(lu->gri, lu->Ml); ALLOC(lu->gri_tmp, lu->Ml); ALLOC(lu->igri, lu->Ml); ALLOC(lu->perm, 2 * v);
     ALLOC(lu->gpivots, v); ALLOC(lu->tagsH, 2 * v); ALLOC(lu->tagsS, 2 * v); ALLOC(lu->hist, lu->M);
