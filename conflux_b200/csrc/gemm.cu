@@ -10,22 +10,36 @@
 // mma.sync.m8n8k4.f64 (DMMA.8x8x4 -- the native FP64 tensor instruction of sm_100a; tcgen05 has no f64 kind)
 // on 64x32 warp tiles with accumulators in registers.  Shared-memory row stride is 132 doubles (== 4 mod 16) so
 // both fragment loads (lane -> [k = lane&3][outer = lane>>2]) are bank-conflict free per half-warp.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace cflx {
 
 namespace {
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, LDT = 132;
-constexpr int NCONS = 8;                    // consumer warps: 2 (m) x 4 (n), warp tile 64 x 32
-constexpr int NTHREADS = (NCONS + 1) * 32;  // + 1 producer warp
-constexpr size_t SMEM_BYTES = (size_t)STAGES * 2 * BK * LDT * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+constexpr int BK = 16, STAGES = 4;
 
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_kernel(GemmArgs g) {
+// WM x WN consumer warps, each owning a 64 x 32 tile of C: CTA tile (64*WM) x (32*WN).
+//   <2,4,1>: 128x128, 8+1 warps, one CTA per SM (largest reuse per byte staged);
+//   <1,4,2>:  64x128, 4+1 warps, TWO CTAs per SM so that one CTA's prologue/epilogue (operand fill, C read-modify-
+//             write) overlaps the other's DMMA main loop.
+template <int WM, int WN>
+struct Cfg {
+    static constexpr int BM = 64 * WM, BN = 32 * WN;
+    static constexpr int LDA = BM + 4, LDB = BN + 4;  // strides == 4 (mod 16) doubles: conflict-free fragment loads
+    static constexpr int NCONS = WM * WN, NTHREADS = (NCONS + 1) * 32;
+    static constexpr size_t SMEM = (size_t)STAGES * BK * (LDA + LDB) * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
+};
+
+template <int WM, int WN, int MINB>
+__global__ void __launch_bounds__(Cfg<WM, WN>::NTHREADS, MINB) gemm_tn_kernel(GemmArgs g) {
+    using C = Cfg<WM, WN>;
+    constexpr int BM = C::BM, BN = C::BN, LDA = C::LDA, LDB = C::LDB, NCONS = C::NCONS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sA = reinterpret_cast<double*>(smem_raw);
-    double* sB = sA + STAGES * BK * LDT;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * BK * LDT);
+    double* sB = sA + STAGES * BK * LDA;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * BK * LDB);
     uint64_t* empty = full + STAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -57,16 +71,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_kernel(GemmArgs g) {
             if (rr < rows) {
                 const int64_t k = (int64_t)kt * BK + rr;
                 if (lane < 16)
-                    bulk_g2s(sA + (s * BK + rr) * LDT, g.AT + k * g.ldat + m0, (uint32_t)(wm * sizeof(double)), &full[s]);
+                    bulk_g2s(sA + (s * BK + rr) * LDA, g.AT + k * g.ldat + m0, (uint32_t)(wm * sizeof(double)), &full[s]);
                 else
-                    bulk_g2s(sB + (s * BK + rr) * LDT, g.B + k * g.ldb + n0, (uint32_t)(wn * sizeof(double)), &full[s]);
+                    bulk_g2s(sB + (s * BK + rr) * LDB, g.B + k * g.ldb + n0, (uint32_t)(wn * sizeof(double)), &full[s]);
             }
         }
         return;
     }
 
     // ===== consumers =====
-    const int wm_off = (warp >> 2) * 64, wn_off = (warp & 3) * 32;
+    const int wm_off = (warp / WN) * 64, wn_off = (warp % WN) * 32;
     const int g4 = lane >> 2, t4 = lane & 3;
     double acc[8][4][2];
 #pragma unroll
@@ -77,17 +91,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_kernel(GemmArgs g) {
     for (int kt = 0; kt < KT; ++kt) {
         const int s = kt % STAGES, u = kt / STAGES;
         mbar_wait(&full[s], u & 1);
-        const double* a_s = sA + s * BK * LDT + wm_off + g4;
-        const double* b_s = sB + s * BK * LDT + wn_off + g4;
+        const double* a_s = sA + s * BK * LDA + wm_off + g4;
+        const double* b_s = sB + s * BK * LDB + wn_off + g4;
         const int rows = min(BK, g.K - kt * BK);
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
             if (kk < rows) {
                 double a[8], b[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) a[i] = a_s[(kk + t4) * LDT + 8 * i];
+                for (int i = 0; i < 8; ++i) a[i] = a_s[(kk + t4) * LDA + 8 * i];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = b_s[(kk + t4) * LDT + 8 * j];
+                for (int j = 0; j < 4; ++j) b[j] = b_s[(kk + t4) * LDB + 8 * j];
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -135,10 +149,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_kernel(GemmArgs g) {
 }
 }  // namespace
 
-int gemm_tn_setup() {
+namespace {
+template <int WM, int WN, int MINB>
+int setup_one() {
     static PerDeviceMax cfg;
-    if (cfg.raise(SMEM_BYTES))
-        CFLX_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    if (cfg.raise(Cfg<WM, WN>::SMEM))
+        CFLX_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<WM, WN, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Cfg<WM, WN>::SMEM));
+    return CFLX_OK;
+}
+template <int WM, int WN, int MINB>
+int launch_one(const GemmArgs& g, cudaStream_t stream) {
+    using C = Cfg<WM, WN>;
+    CFLX_TRY((setup_one<WM, WN, MINB>()));
+    dim3 grid((g.N + C::BN - 1) / C::BN, (g.M + C::BM - 1) / C::BM);
+    gemm_tn_kernel<WM, WN, MINB><<<grid, C::NTHREADS, C::SMEM, stream>>>(g);
+    CFLX_CUDA(cudaGetLastError());
+    return CFLX_OK;
+}
+int tile_variant() {  // CFLX_GEMM_TILE=128 selects the single-CTA-per-SM 128x128 tile, default 64x128 x 2 CTAs/SM
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("CFLX_GEMM_TILE");
+        v = (e && atoi(e) == 128) ? 128 : 64;
+    }
+    return v;
+}
+}  // namespace
+
+int gemm_tn_setup() {
+    CFLX_TRY((setup_one<2, 4, 1>()));
+    CFLX_TRY((setup_one<1, 4, 2>()));
     return CFLX_OK;
 }
 
@@ -151,11 +192,8 @@ int launch_gemm_tn(const GemmArgs& g, cudaStream_t stream) {
                        (long long)g.ldat, (long long)g.ldb, (long long)g.ldc, (long long)g.ldd);
         return CFLX_ERR_UNSUPPORTED;
     }
-    CFLX_TRY(gemm_tn_setup());
-    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
-    gemm_tn_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(g);
-    CFLX_CUDA(cudaGetLastError());
-    return CFLX_OK;
+    if (tile_variant() == 128 && g.M > 64) return launch_one<2, 4, 1>(g, stream);
+    return launch_one<1, 4, 2>(g, stream);
 }
 
 }  // namespace cflx

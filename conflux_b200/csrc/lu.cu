@@ -697,19 +697,20 @@ int cflx_lu_create(cflx_comm* c, int M, int N, int v, int Px, int Py, int Pz, cf
     if ((rc = gemm_tn_setup())) return fail(rc);
     lu->h_hist.assign(lu->M, -1);
     {
-        // look-ahead: pivot search of iteration k+1 on a high-priority side stream, on a capped number of SMs, while
-        // the trailing update of iteration k runs on the rest.  (Enabled on single-rank grids; multi-rank grids keep
-        // one stream so that all NCCL calls of a rank stay in one order.)
+        // look-ahead: pivot search of iteration k+1 (extract, layer reduce, local search, tournament exchanges) on a
+        // high-priority side stream, on a capped number of SMs, while the trailing update of iteration k runs on the
+        // rest.  A rank never has NCCL work in flight on both streams: the side stream's collectives (k- and
+        // i-communicator) sit between the fork after GEMM_next and the join before the next world broadcast.
         const char* e = getenv("CFLX_LOOKAHEAD");
         const bool want = e ? atoi(e) != 0 : true;
-        if (want && lu->P == 1) {
+        if (want) {
             int lo = 0, hi = 0;
             cudaDeviceGetStreamPriorityRange(&lo, &hi);
             if (cudaStreamCreateWithPriority(&lu->side, cudaStreamNonBlocking, hi) != cudaSuccess) return fail(CFLX_ERR_CUDA);
             if (cudaEventCreateWithFlags(&lu->ev_fork, cudaEventDisableTiming) != cudaSuccess) return fail(CFLX_ERR_CUDA);
             if (cudaEventCreateWithFlags(&lu->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail(CFLX_ERR_CUDA);
             const char* c = getenv("CFLX_PANEL_CTAS");
-            lu->pws.cta_cap = c ? atoi(c) : 32;
+            lu->pws.cta_cap = c ? atoi(c) : (lu->P == 1 ? 32 : 48);
         }
     }
     // zero the panels once: padded columns are read (and masked) by the GEMM producer
@@ -772,8 +773,19 @@ int cflx_lu_factor(cflx_lu* lu, double* ms_out) {
         for (auto& e : lu->ev) CFLX_CUDA(cudaEventCreate(&e));
     }
     lu->ev_used.assign(2 * lu->Nt, 0);
-    int rc0 = panel_phase(lu, 0, 0, s);
-    if (rc0 != CFLX_OK) return rc0;
+    {
+        cudaStream_t side = lu->profiling ? nullptr : lu->side;
+        if (side) {
+            CFLX_CUDA(cudaEventRecord(lu->ev_fork, s));
+            CFLX_CUDA(cudaStreamWaitEvent(side, lu->ev_fork, 0));
+        }
+        int rc0 = panel_phase(lu, 0, 0, side ? side : s);
+        if (rc0 != CFLX_OK) return rc0;
+        if (side) {
+            CFLX_CUDA(cudaEventRecord(lu->ev_join, side));
+            CFLX_CUDA(cudaStreamWaitEvent(s, lu->ev_join, 0));
+        }
+    }
     for (int k = 0; k < lu->Nt; ++k) {
         int rc = finish_step(lu, k, fnpr);
         if (rc != CFLX_OK) {
