@@ -241,6 +241,7 @@ def main():
 
     # ---- parity of the run that was just timed ----------------------------------------------------------------
     ok_perm = sorted(perm.tolist()) == list(range(gv.M))
+    resid = cb.residual(gv) if world == 1 else None   # ||PA-LU||_F/||A||_F on the device, full BASELINE size
 
     if rank == 0:
         dmma_peak = peak_burst
@@ -267,7 +268,8 @@ def main():
                                         "MEASURED_PEAKS.json has no FP64 entry; nominal %.0f TFLOP/s" % FP64_TENSOR_NOMINAL_TFLOPS,
                          "share_of_step": gemm_ms / dev_ms if dev_ms else None,
                          "whole_path_frac": value / 1e3 / (args.gpus * dmma_peak)},
-            "parity": {"permutation_is_permutation": bool(ok_perm)},
+            "parity": {"permutation_is_permutation": bool(ok_perm), "residual_PA_minus_LU_rel_frobenius": resid,
+                       "residual_tolerance": 1e-12},
         }
         if args.gpus == 1 and not args.no_cpu_baseline:
             cores = cpu_threads()

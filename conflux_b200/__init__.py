@@ -15,7 +15,7 @@ import numpy as np
 
 from ._lib import ConfluxError, LIB_PATH, SYMBOLS, check, lib
 
-__all__ = ["pinned_empty", "pinned_free", "Comm", "lu_params", "LU_rep", "auto_grid", "lu_dims", "init_matrix_host", "ConfluxError", "dbg"]
+__all__ = ["pinned_empty", "pinned_free", "Comm", "lu_params", "LU_rep", "residual", "auto_grid", "lu_dims", "init_matrix_host", "ConfluxError", "dbg"]
 
 
 def auto_grid(M, N, P):
@@ -169,6 +169,13 @@ def LU_rep(gv, C=None, permutation=None, upload=True):
         assert permutation.dtype == np.int32 and permutation.size >= gv.M
         check(lib().cflx_lu_get_permutation(gv._h, permutation.ctypes.data), "lu_get_permutation")
     return ms.value
+
+
+def residual(gv):
+    """||PA - LU||_F / ||A||_F of the last LU_rep, computed on the GPU (single-rank grids)."""
+    r = ctypes.c_double()
+    check(lib().cflx_lu_residual(gv._h, ctypes.byref(r)), "lu_residual")
+    return r.value
 
 
 class dbg:

@@ -89,6 +89,10 @@ int launch_store_u_rows(double* A, int64_t lda, int fnpr_old, MovePlan plan, con
                         int ncols, int v, cudaStream_t stream);
 int launch_store_diag(double* A, int64_t lda, int fnpr_old, MovePlan plan, const double* A00, int loff, int v,
                       cudaStream_t stream);
+// residual helpers (validation only)
+int launch_split_factors(const double* F, int64_t ldf, int n, double* LT, double* U, cudaStream_t stream);
+int launch_gather_perm_rows(const double* A, int64_t lda, const int* perm, int n, double* out, cudaStream_t stream);
+int launch_sumsq(const double* X, int64_t count, double* out, cudaStream_t stream);
 // misc
 int launch_fill(double* p, int64_t n, double val, cudaStream_t stream);
 int launch_iota_gri(int* gri, int* igri, int Ml, int v, int Px, int pi, cudaStream_t stream);

@@ -900,6 +900,62 @@ int cflx_lu_get_factors(cflx_lu* lu, double* C_host, int* perm_out) {
     return CFLX_OK;
 }
 
+// ||P A - L U||_F / ||A||_F on the device, with the library's own GEMM.  Single-rank grids only (the factors of a
+// multi-rank grid are validated on the host from cflx_lu_get_factors, see tests/).
+int cflx_lu_residual(cflx_lu* lu, double* rel_out) {
+    if (!lu || !rel_out) return CFLX_ERR_ARG;
+    if (!lu->factored) {
+        set_last_error("residual requested before cflx_lu_factor");
+        return CFLX_ERR_STATE;
+    }
+    if (lu->P != 1) {
+        set_last_error("cflx_lu_residual supports single-rank grids; use cflx_lu_get_factors + a host check otherwise");
+        return CFLX_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = lu->comm->stream;
+    CFLX_CUDA(cudaSetDevice(lu->comm->device));
+    const int n = lu->N;
+    const size_t nn = (size_t)n * n;
+    double *LT = nullptr, *U = nullptr, *PA = nullptr, *acc = nullptr;
+    int rc = CFLX_OK;
+    auto cleanup = [&]() {
+        cudaFree(LT);
+        cudaFree(U);
+        cudaFree(PA);
+        cudaFree(acc);
+    };
+    if ((rc = dmalloc(&LT, nn)) || (rc = dmalloc(&U, nn)) || (rc = dmalloc(&PA, nn)) || (rc = dmalloc(&acc, 2))) {
+        cleanup();
+        return rc;
+    }
+    // at Px == 1 local row r of A11 is pivoted row r (rows were promoted in pivot order)
+    rc = launch_split_factors(lu->A11, lu->Nl, n, LT, U, s);
+    if (!rc) rc = launch_gather_perm_rows(lu->A0, lu->Nl, lu->hist, n, PA, s);
+    if (!rc && cudaMemsetAsync(acc, 0, 2 * sizeof(double), s) != cudaSuccess) rc = CFLX_ERR_CUDA;
+    if (!rc) {
+        GemmArgs g{};
+        g.M = n; g.N = n; g.K = n;
+        g.AT = LT; g.ldat = n;
+        g.B = U; g.ldb = n;
+        g.C = PA; g.ldc = n;
+        g.D = PA; g.ldd = n;
+        g.alpha = -1.0; g.beta = 1.0;
+        rc = launch_gemm_tn(g, s);
+    }
+    if (!rc) rc = launch_sumsq(PA, (int64_t)nn, acc, s);
+    if (!rc) rc = launch_sumsq(lu->A0, (int64_t)nn, acc + 1, s);
+    double h[2] = {0, 0};
+    if (!rc && cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = CFLX_ERR_CUDA;
+    if (!rc && cudaStreamSynchronize(s) != cudaSuccess) {
+        set_last_error("residual: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = CFLX_ERR_CUDA;
+    }
+    cleanup();
+    if (rc) return rc;
+    *rel_out = std::sqrt(h[0]) / std::sqrt(h[1]);
+    return CFLX_OK;
+}
+
 int cflx_host_alloc(size_t bytes, void** out) {
     if (!out) return CFLX_ERR_ARG;
     int n = 0;

@@ -20,6 +20,7 @@
 #include <cooperative_groups.h>
 
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -55,6 +56,16 @@ __device__ __forceinline__ uint4 ld_ll2(const uint2* p) {  // two consecutive LL
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
+
+// ---- thread-block-cluster helpers (DSMEM exchange for small panels) ----
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_dsmem_b64(const void* local_smem_ptr, unsigned peer_cta, unsigned long long v) {
+    unsigned remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(peer_cta));
+    asm volatile("st.shared::cluster.b64 [%0], %1;" ::"r"(remote), "l"(v) : "memory");
+}
+constexpr int CS_MAX = 16;  // non-portable cluster size limit on B200
 
 struct Cand {
     unsigned long long key;  // bits of |a| (monotone for non-negative doubles)
@@ -103,7 +114,7 @@ __device__ __forceinline__ Cand block_argmax(Cand c, unsigned long long* red_key
     return best;
 }
 
-template <int NB, int RPT_MAX>
+template <int NB, int RPT_MAX, bool CLUSTER>
 __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Ab = reinterpret_cast<double*>(smem_raw);  // [NB][Rpad] inner block, column-major per CTA
@@ -114,6 +125,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
     int* red_pos = reinterpret_cast<int*>(red_key + 2 * PT_WARPS);
     int* red_row = red_pos + 2 * PT_WARPS;
     int* pivrow_blk = red_row + 2 * PT_WARPS;  // [NB]
+    // cluster mode: candidate slots written by every CTA of the cluster straight into my shared memory
+    // cslot[parity][cta][0] = key, [1] = pos | row << 32, [2..2+NB) = the candidate's inner-block row
+    unsigned long long* cslot = reinterpret_cast<unsigned long long*>(pivrow_blk + NB + (NB & 1));
     int rb = 0;
 
     const int t = threadIdx.x;
@@ -169,55 +183,90 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
             }
             const Cand mine = block_argmax(c, red_key, red_pos, red_row, rb);
             TICK(0)
-            // publish my CTA's candidate and its inner-block row (LL words, fire and forget)
             const int par = jg & 1;
-            const unsigned epoch = (unsigned)(p.epoch_base + jg + 1);
-            uint2* myhdr = p.slot_hdr + (size_t)(par * MAXG + cta) * 4;
-            if (t < 4) {
-                const unsigned w = t == 0 ? (unsigned)mine.key : t == 1 ? (unsigned)(mine.key >> 32)
-                                 : t == 2 ? (unsigned)mine.pos : (unsigned)mine.row;
-                st_ll(myhdr + t, w, epoch);
-            }
-            if (mine.row >= 0 && t < nbc) {
-                const unsigned long long x = (unsigned long long)__double_as_longlong(Ab[t * Rpad + (mine.row - row_base)]);
-                uint2* myrow = p.slot_rows + (size_t)(par * MAXG + cta) * 64 + 2 * t;
-                st_ll(myrow, (unsigned)x, epoch);
-                st_ll(myrow + 1, (unsigned)(x >> 32), epoch);
-            }
-            // gather every CTA's candidate
-            Cand gc{0ull, INT_MAX, -1};
-            for (int g = t; g < p.G; g += PT_THREADS) {
-                const uint2* h = p.slot_hdr + (size_t)(par * MAXG + g) * 4;
-                uint4 a, b;
-                do {
-                    a = ld_ll2(h);
-                    b = ld_ll2(h + 2);
-                } while (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch);
-                Cand o{((unsigned long long)a.z << 32) | a.x, (int)b.x, (int)b.z};
-                if (better(o, gc)) gc = o;
-            }
-            TICK(1)
-            const Cand win = block_argmax(gc, red_key, red_pos, red_row, rb);
-            TICK(2)
-            // (win.row < 0 cannot happen while jg < nsteps = min(n, v): some row is still active)
-            const int wcta = win.row / p.R;
-            if (t < nbc) {
-                const uint2* wr = p.slot_rows + (size_t)(par * MAXG + wcta) * 64 + 2 * t;
-                uint4 a;
-                do {
-                    a = ld_ll2(wr);
-                } while (a.y != epoch || a.w != epoch);
-                const double x = __longlong_as_double((long long)(((unsigned long long)a.z << 32) | a.x));
-                prow[t] = x;
-                LU11[j * (NB + 1) + t] = x;
+            Cand win;
+            const double* pr;  // the winner's inner-block row
+            if constexpr (CLUSTER) {
+                // every CTA deposits {key, pos|row, row values} into the slot [par][cta] of EVERY CTA of the cluster
+                // (DSMEM stores), one cluster barrier, then each warp picks the winner from its own shared memory
+                unsigned long long* myslot = cslot + (size_t)(par * CS_MAX + cta) * (NB + 2);
+                const int words = nbc + 2;
+                const int lrw = mine.row >= 0 ? mine.row - row_base : 0;
+                for (int e = t; e < p.G * words; e += PT_THREADS) {
+                    const int peer = e / words, w = e % words;
+                    unsigned long long val;
+                    if (w == 0) val = mine.key;
+                    else if (w == 1) val = (unsigned long long)(unsigned)mine.pos | ((unsigned long long)(unsigned)mine.row << 32);
+                    else val = (unsigned long long)__double_as_longlong(Ab[(w - 2) * Rpad + lrw]);
+                    st_dsmem_b64(myslot + w, (unsigned)peer, val);
+                }
+                cluster_arrive_release();
+                cluster_wait_acquire();
+                TICK(1)
+                Cand gc{0ull, INT_MAX, -1};
+                const int lane = t & 31;
+                if (lane < p.G) {
+                    const unsigned long long* sl = cslot + (size_t)(par * CS_MAX + lane) * (NB + 2);
+                    const unsigned long long pr2 = sl[1];
+                    gc = Cand{sl[0], (int)(unsigned)pr2, (int)(unsigned)(pr2 >> 32)};
+                }
+                win = warp_argmax(gc);
+                TICK(2)
+                const int wcta = win.row / p.R;
+                pr = reinterpret_cast<const double*>(cslot + (size_t)(par * CS_MAX + wcta) * (NB + 2) + 2);
+                if (t < nbc) LU11[j * (NB + 1) + t] = pr[t];
+            } else {
+                // publish my CTA's candidate and its inner-block row (LL words, fire and forget)
+                const unsigned epoch = (unsigned)(p.epoch_base + jg + 1);
+                uint2* myhdr = p.slot_hdr + (size_t)(par * MAXG + cta) * 4;
+                if (t < 4) {
+                    const unsigned w = t == 0 ? (unsigned)mine.key : t == 1 ? (unsigned)(mine.key >> 32)
+                                     : t == 2 ? (unsigned)mine.pos : (unsigned)mine.row;
+                    st_ll(myhdr + t, w, epoch);
+                }
+                if (mine.row >= 0 && t < nbc) {
+                    const unsigned long long x = (unsigned long long)__double_as_longlong(Ab[t * Rpad + (mine.row - row_base)]);
+                    uint2* myrow = p.slot_rows + (size_t)(par * MAXG + cta) * 64 + 2 * t;
+                    st_ll(myrow, (unsigned)x, epoch);
+                    st_ll(myrow + 1, (unsigned)(x >> 32), epoch);
+                }
+                // gather every CTA's candidate
+                Cand gc{0ull, INT_MAX, -1};
+                for (int g = t; g < p.G; g += PT_THREADS) {
+                    const uint2* h = p.slot_hdr + (size_t)(par * MAXG + g) * 4;
+                    uint4 a, b;
+                    do {
+                        a = ld_ll2(h);
+                        b = ld_ll2(h + 2);
+                    } while (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch);
+                    Cand o{((unsigned long long)a.z << 32) | a.x, (int)b.x, (int)b.z};
+                    if (better(o, gc)) gc = o;
+                }
+                TICK(1)
+                win = block_argmax(gc, red_key, red_pos, red_row, rb);
+                TICK(2)
+                // (win.row < 0 cannot happen while jg < nsteps = min(n, v): some row is still active)
+                const int wcta = win.row / p.R;
+                if (t < nbc) {
+                    const uint2* wr = p.slot_rows + (size_t)(par * MAXG + wcta) * 64 + 2 * t;
+                    uint4 a;
+                    do {
+                        a = ld_ll2(wr);
+                    } while (a.y != epoch || a.w != epoch);
+                    const double x = __longlong_as_double((long long)(((unsigned long long)a.z << 32) | a.x));
+                    prow[t] = x;
+                    LU11[j * (NB + 1) + t] = x;
+                }
+
+                pr = prow;
             }
             if (t == 0) {
                 pivrow_blk[j] = win.row;
                 if (cta == 0) p.perm_out[jg] = win.row;
             }
-            __syncthreads();
+            if constexpr (!CLUSTER) __syncthreads();
             TICK(3)
-            const double pivot = prow[j];
+            const double pivot = pr[j];
             const double rinv = pivot != 0.0 ? 1.0 / pivot : 0.0;
             double lq[RPT_MAX];
 #pragma unroll
@@ -237,7 +286,6 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                 }
             }
             {
-                const double* __restrict__ pr = prow;
                 double* __restrict__ ab = Ab;
 #pragma unroll 4
                 for (int c2 = j + 1; c2 < nbc; ++c2) {
@@ -348,27 +396,50 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
 template <int NB>
 size_t panel_smem_bytes(int Rpad, int v) {
     return ((size_t)NB * Rpad + (size_t)NB * v + NB * (NB + 1) + NB) * sizeof(double) +
-           2 * PT_WARPS * (sizeof(unsigned long long) + 2 * sizeof(int)) + NB * sizeof(int) + 64;
+           2 * PT_WARPS * (sizeof(unsigned long long) + 2 * sizeof(int)) + (NB + 2) * sizeof(int) +
+           2 * CS_MAX * (NB + 2) * sizeof(unsigned long long) + 64;
 }
 
 template <int NB, int RPT>
-int launch_nb_rpt(PanelArgs& a, cudaStream_t stream) {
+int launch_nb_rpt(PanelArgs& a, bool cluster, cudaStream_t stream) {
     const size_t smem = panel_smem_bytes<NB>(a.Rpad, a.v);
+    void* params[] = {&a};
+    if (cluster) {
+        // one thread-block cluster of G (<= 16) CTAs: candidates are exchanged through distributed shared memory
+        static PerDeviceMax cfg;
+        if (cfg.raise(smem)) {
+            CFLX_CUDA(cudaFuncSetAttribute(panel_getrf_kernel<NB, RPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CFLX_CUDA(cudaFuncSetAttribute(panel_getrf_kernel<NB, RPT, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        }
+        cudaLaunchConfig_t cfgl{};
+        cfgl.gridDim = dim3(a.G);
+        cfgl.blockDim = dim3(PT_THREADS);
+        cfgl.dynamicSmemBytes = smem;
+        cfgl.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = a.G;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfgl.attrs = at;
+        cfgl.numAttrs = 1;
+        if (cudaLaunchKernelExC(&cfgl, (const void*)panel_getrf_kernel<NB, RPT, true>, params) == cudaSuccess) return CFLX_OK;
+        cudaGetLastError();  // cluster shape not launchable here: fall through to the grid-wide (LL exchange) variant
+    }
     static PerDeviceMax cfg;
     if (cfg.raise(smem))
-        CFLX_CUDA(cudaFuncSetAttribute(panel_getrf_kernel<NB, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    void* params[] = {&a};
-    CFLX_CUDA(cudaLaunchCooperativeKernel((void*)panel_getrf_kernel<NB, RPT>, dim3(a.G), dim3(PT_THREADS), params, smem,
+        CFLX_CUDA(cudaFuncSetAttribute(panel_getrf_kernel<NB, RPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CFLX_CUDA(cudaLaunchCooperativeKernel((void*)panel_getrf_kernel<NB, RPT, false>, dim3(a.G), dim3(PT_THREADS), params, smem,
                                           stream));
     return CFLX_OK;
 }
 template <int NB>
-int launch_nb(PanelArgs& a, cudaStream_t stream) {
+int launch_nb(PanelArgs& a, bool cluster, cudaStream_t stream) {
     const int rpt = (a.R + PT_THREADS - 1) / PT_THREADS;
-    if (rpt <= 1) return launch_nb_rpt<NB, 1>(a, stream);
-    if (rpt <= 2) return launch_nb_rpt<NB, 2>(a, stream);
-    if (rpt <= 4) return launch_nb_rpt<NB, 4>(a, stream);
-    return launch_nb_rpt<NB, 8>(a, stream);
+    if (rpt <= 1) return launch_nb_rpt<NB, 1>(a, cluster, stream);
+    if (rpt <= 2) return launch_nb_rpt<NB, 2>(a, cluster, stream);
+    if (rpt <= 4) return launch_nb_rpt<NB, 4>(a, cluster, stream);
+    return launch_nb_rpt<NB, 8>(a, cluster, stream);
 }
 }  // namespace
 
@@ -405,10 +476,20 @@ int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, 
     a.n = n;
     a.v = v;
     a.nsteps = n < v ? n : v;
+    // Small panels (late steps, tournament stacks) are latency-bound by the per-column exchange: run them as ONE
+    // cluster of <= 16 CTAs that exchanges candidates through distributed shared memory.  CFLX_CLUSTER_ROWS sets the
+    // largest n handled that way (0 disables).
+    static int cluster_rows = -1;
+    if (cluster_rows < 0) {
+        const char* e = getenv("CFLX_CLUSTER_ROWS");
+        cluster_rows = e ? atoi(e) : 6144;
+    }
+    const bool cluster = (n <= cluster_rows) && (n <= CS_MAX * RPT_LIMIT * PT_THREADS);
     int G = (n + PT_THREADS - 1) / PT_THREADS;
     if (G < 1) G = 1;
     if (G > ws->max_ctas) G = ws->max_ctas;
     if (ws->cta_cap > 0 && G > ws->cta_cap) G = ws->cta_cap;
+    if (cluster && G > CS_MAX) G = CS_MAX;
     int R = (n + G - 1) / G;
     R = (int)round_up(R > 0 ? R : 1, 32);
     G = n > 0 ? (n + R - 1) / R : 1;
@@ -432,10 +513,10 @@ int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, 
     if (nb == 16 && panel_smem_bytes<16>(a.Rpad, v) > budget) nb = 8;
     if (nb_used) *nb_used = nb;
     switch (nb) {
-        case 32: return launch_nb<32>(a, stream);
-        case 16: return launch_nb<16>(a, stream);
-        case 8: return launch_nb<8>(a, stream);
-        default: return launch_nb<4>(a, stream);
+        case 32: return launch_nb<32>(a, cluster, stream);
+        case 16: return launch_nb<16>(a, cluster, stream);
+        case 8: return launch_nb<8>(a, cluster, stream);
+        default: return launch_nb<4>(a, cluster, stream);
     }
 }
 

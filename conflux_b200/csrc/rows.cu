@@ -10,6 +10,8 @@
 //   conflux_opt.hpp:1137-1147         pivot-row extract into A01BuffTemp                -> fused into push_phase1
 //   conflux_opt.hpp:1680-1771         validation stores of L / U / A00                  -> store_panel_T,
 //                                                                                         store_u_rows, store_diag
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -253,6 +255,47 @@ __global__ void record_pivots_kernel(const int* gpivots, int v, int* hist, int k
     if (i < v) hist[(int64_t)k * v + i] = gpivots[i];
 }
 
+// ---------------------------------------------------------------- residual helpers (validation, not on the hot path)
+// LT[k][m] = L[m][k] (unit lower of the packed factors F, row-major n x n), U[k][c] = upper part
+__global__ void split_factors_kernel(const double* __restrict__ F, int64_t ldf, int n, double* __restrict__ LT,
+                                     double* __restrict__ U) {
+    __shared__ double tile[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const int r = r0 + dy, c = c0 + threadIdx.x;
+        double x = 0.0;
+        if (r < n && c < n) x = F[(int64_t)r * ldf + c];
+        tile[dy][threadIdx.x] = x;
+        if (r < n && c < n) U[(int64_t)r * n + c] = (c >= r) ? x : 0.0;
+    }
+    __syncthreads();
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const int k = c0 + dy, m = r0 + threadIdx.x;  // LT[k][m] = L[m][k]
+        if (k < n && m < n) LT[(int64_t)k * n + m] = (m > k) ? tile[threadIdx.x][dy] : (m == k ? 1.0 : 0.0);
+    }
+}
+__global__ void gather_perm_rows_kernel(const double* __restrict__ A, int64_t lda, const int* __restrict__ perm, int n,
+                                        double* __restrict__ out) {
+    const int r = blockIdx.x;
+    const double* src = A + (int64_t)perm[r] * lda;
+    double* dst = out + (int64_t)r * n;
+    for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < n; c += gridDim.y * blockDim.x) dst[c] = src[c];
+}
+__global__ void sumsq_kernel(const double* __restrict__ X, int64_t count, double* __restrict__ out) {
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        s = fma(X[i], X[i], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ double w[32];
+    if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? w[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) atomicAdd(out, s);
+    }
+}
+
 inline int row_chunks(int len) {
     int c = (len / 2 + 2047) / 2048;  // ~16 KB of double2 per CTA-chunk
     return c < 1 ? 1 : (c > 64 ? 64 : c);
@@ -341,6 +384,20 @@ int launch_store_diag(double* A, int64_t lda, int fnpr_old, MovePlan plan, const
                       cudaStream_t s) {
     dim3 grid(1, v);
     store_diag_kernel<<<grid, 128, 0, s>>>(A, lda, fnpr_old, plan, A00, loff, v);
+    POST_LAUNCH();
+}
+int launch_split_factors(const double* F, int64_t ldf, int n, double* LT, double* U, cudaStream_t s) {
+    dim3 grid((n + 31) / 32, (n + 31) / 32), block(32, 8);  // n <= 2M rows
+    split_factors_kernel<<<grid, block, 0, s>>>(F, ldf, n, LT, U);
+    POST_LAUNCH();
+}
+int launch_gather_perm_rows(const double* A, int64_t lda, const int* perm, int n, double* out, cudaStream_t s) {
+    dim3 grid(n, std::max(1, std::min(32, n / 256)));
+    gather_perm_rows_kernel<<<grid, 256, 0, s>>>(A, lda, perm, n, out);
+    POST_LAUNCH();
+}
+int launch_sumsq(const double* X, int64_t count, double* out, cudaStream_t s) {
+    sumsq_kernel<<<1184, 256, 0, s>>>(X, count, out);
     POST_LAUNCH();
 }
 int launch_fill(double* p, int64_t n, double val, cudaStream_t s) {

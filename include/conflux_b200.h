@@ -82,6 +82,9 @@ int cflx_lu_factor(cflx_lu*, double* ms_out);
 int cflx_lu_get_factors(cflx_lu*, double* C_host, int* permutation_out);
 /* device -> host copy of the permutation only (the cheap "result" of a run) */
 int cflx_lu_get_permutation(cflx_lu*, int* permutation_out);
+/* ||P*A - L*U||_F / ||A||_F computed on the device with the library's own GEMM (single-rank grids; allocates 3 n^2
+ * doubles temporarily).  The reference prints the absolute norm in its validation build (conflux_miniapp.cpp:494-500). */
+int cflx_lu_residual(cflx_lu*, double* rel_out);
 /* number of kernels this plan launched since the last call (for bench.py's gpu_launches) */
 int cflx_lu_launch_count(cflx_lu*, int64_t* count_out, int reset);
 /* per-phase device time of the last cflx_lu_factor when profiling was enabled: ms_out[8] =

@@ -66,6 +66,20 @@ def test_single_gpu_larger_residual_property():
     assert np.abs(np.tril(LU, -1)).max() <= 1.0 + 1e-12          # partial pivoting inside each panel: |l| <= 1
 
 
+def test_device_residual_matches_host_residual():
+    import conflux_b200 as cb
+    comm = cb.Comm(1, 0, None, 0)
+    gv = cb.lu_params(1024, 1024, 128, 1, 1, 1, comm)
+    C = np.zeros((gv.Ml, gv.Nl))
+    perm = np.zeros(gv.M, dtype=np.int32)
+    cb.LU_rep(gv, C, perm)
+    dev = cb.residual(gv)
+    host = layout.residual(gv.data, C, perm)
+    assert dev <= RESIDUAL_TOL and abs(dev - host) <= 0.2 * host + 1e-17
+    gv.free_comms()
+    comm.close()
+
+
 def test_repeat_is_deterministic_and_input_untouched():
     a = gpu_lu(512, 64)
     b = gpu_lu(512, 64)
