@@ -167,11 +167,11 @@ int launch_one(const GemmArgs& g, cudaStream_t stream) {
     CFLX_CUDA(cudaGetLastError());
     return CFLX_OK;
 }
-int tile_variant() {  // CFLX_GEMM_TILE=128 selects the single-CTA-per-SM 128x128 tile, default 64x128 x 2 CTAs/SM
+int tile_variant() {  // CFLX_GEMM_TILE=64 selects the 64x128 tile with two CTAs per SM; default 128x128, one CTA per SM
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("CFLX_GEMM_TILE");
-        v = (e && atoi(e) == 128) ? 128 : 64;
+        v = (e && atoi(e) == 64) ? 64 : 128;
     }
     return v;
 }

@@ -482,7 +482,7 @@ int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, 
     static int cluster_rows = -1;
     if (cluster_rows < 0) {
         const char* e = getenv("CFLX_CLUSTER_ROWS");
-        cluster_rows = e ? atoi(e) : 6144;
+        cluster_rows = e ? atoi(e) : 0;  // opt-in until validated on hardware
     }
     const bool cluster = (n <= cluster_rows) && (n <= CS_MAX * RPT_LIMIT * PT_THREADS);
     int G = (n + PT_THREADS - 1) / PT_THREADS;
