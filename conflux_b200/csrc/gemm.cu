@@ -192,8 +192,8 @@ int launch_gemm_tn(const GemmArgs& g, cudaStream_t stream) {
                        (long long)g.ldat, (long long)g.ldb, (long long)g.ldc, (long long)g.ldd);
         return CFLX_ERR_UNSUPPORTED;
     }
-    if (tile_variant() == 128 && g.M > 64) return launch_one<2, 4, 1>(g, stream);
-    return launch_one<1, 4, 2>(g, stream);
+    if (tile_variant() == 64) return launch_one<1, 4, 2>(g, stream);
+    return launch_one<2, 4, 1>(g, stream);
 }
 
 }  // namespace cflx
