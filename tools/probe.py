@@ -12,7 +12,7 @@ for (M, N, K) in [(16128, 16128, 256), (8192, 8192, 512)]:
     AT, B = rng.standard_normal((K, M)), rng.standard_normal((K, N))
     _, ms = cb.dbg.gemm_tn(AT, B, None, -1.0, 1.0, reps=5)
     print(f"gemm_tn M={M} N={N} K={K}: {ms:.3f} ms  {2.0*M*N*K/ms/1e9:.2f} TFLOP/s", flush=True)
-for (n, v) in [(2048, 256), (16384, 256), (32768, 512), (1024, 512)]:
+for (n, v) in [(2048, 256), (4096, 256), (16384, 256), (32768, 512), (1024, 512)]:
     P = 5.0 + rng.random((n, v))
     _, _, _, ms = cb.dbg.panel(P, reps=3)
     import ctypes
@@ -22,7 +22,7 @@ for (n, v) in [(2048, 256), (16384, 256), (32768, 512), (1024, 512)]:
     print(f"panel n={n} v={v}: {ms:.3f} ms ({ms/v*1e3:.2f} us/column)  CTA0 kcycles: " +
           ", ".join(f"{a}={c/1e3:.0f}" for a, c in zip(names, cyc)), flush=True)
 comm = cb.Comm(1, 0, None, 0)
-cfgs = [(la, ctas, N, v) for (N, v) in [(8192, 256), (16384, 256)] for (la, ctas) in [(1, 24), (1, 32), (1, 48)]]
+cfgs = [(1, 32, 8192, 256), (1, 32, 16384, 256)]
 for (la, ctas, N, v) in cfgs:
     os.environ["CFLX_LOOKAHEAD"] = str(la)
     os.environ["CFLX_PANEL_CTAS"] = str(ctas)
