@@ -6,8 +6,6 @@ import socket
 
 import numpy as np
 import pytest
-import torch.distributed as dist
-import torch.multiprocessing as mp
 
 
 def _free_port():
@@ -19,6 +17,7 @@ def _free_port():
 
 
 def _worker(rank, world, port, q):
+    import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import conflux_b200 as cb
@@ -47,6 +46,7 @@ def _worker(rank, world, port, q):
 
 
 def test_two_rank_host_plumbing():
+    import torch.multiprocessing as mp   # (torch is imported lazily: GPU-marked collection must stay fast)
     import conflux_b200 as cb
     import ctypes
     n = ctypes.c_int()
