@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
     int* pivrow_blk = red_row + 2 * PT_WARPS;  // [NB]
     // cluster mode: candidate slots written by every CTA of the cluster straight into my shared memory
     // cslot[parity][cta][0] = key, [1] = pos | row << 32, [2..2+NB) = the candidate's inner-block row
-    unsigned long long* cslot = reinterpret_cast<unsigned long long*>(pivrow_blk + NB + (NB & 1));
+    int* win_sh = pivrow_blk + NB;  // [2] winner {pos, row} broadcast by warp 0 (grid mode)
+    unsigned long long* cslot = reinterpret_cast<unsigned long long*>(pivrow_blk + NB + 2 + (NB & 1));
     int rb = 0;
 
     const int t = threadIdx.x;
@@ -230,41 +231,52 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                     st_ll(myrow, (unsigned)x, epoch);
                     st_ll(myrow + 1, (unsigned)(x >> 32), epoch);
                 }
-                // gather every CTA's candidate
-                Cand gc{0ull, INT_MAX, -1};
-                for (int g = t; g < p.G; g += PT_THREADS) {
-                    const uint2* h = p.slot_hdr + (size_t)(par * MAXG + g) * 4;
-                    uint4 a, b;
-                    do {
-                        a = ld_ll2(h);
-                        b = ld_ll2(h + 2);
-                    } while (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch);
-                    Cand o{((unsigned long long)a.z << 32) | a.x, (int)b.x, (int)b.z};
-                    if (better(o, gc)) gc = o;
+                // warp 0 alone gathers every CTA's candidate, picks the winner (warp-level argmax, no block barrier) and
+                // fetches the winner's inner-block row; the other warps wait at the single barrier below
+                if (t < 32) {
+                    Cand gc{0ull, INT_MAX, -1};
+                    for (int g = t; g < p.G; g += 32) {
+                        const uint2* h = p.slot_hdr + (size_t)(par * MAXG + g) * 4;
+                        uint4 a, b;
+                        do {
+                            a = ld_ll2(h);
+                            b = ld_ll2(h + 2);
+                        } while (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch);
+                        Cand o{((unsigned long long)a.z << 32) | a.x, (int)b.x, (int)b.z};
+                        if (better(o, gc)) gc = o;
+                    }
+                    TICK(1)
+                    const Cand w = warp_argmax(gc);
+                    TICK(2)
+                    // (w.row < 0 cannot happen while jg < nsteps = min(n, v): some row is still active)
+                    const int wcta = w.row / p.R;
+                    if (t < nbc) {
+                        const uint2* wr = p.slot_rows + (size_t)(par * MAXG + wcta) * 64 + 2 * t;
+                        uint4 a;
+                        do {
+                            a = ld_ll2(wr);
+                        } while (a.y != epoch || a.w != epoch);
+                        const double x = __longlong_as_double((long long)(((unsigned long long)a.z << 32) | a.x));
+                        prow[t] = x;
+                        LU11[j * (NB + 1) + t] = x;
+                    }
+                    if (t == 0) {
+                        win_sh[0] = w.pos;
+                        win_sh[1] = w.row;
+                    }
                 }
-                TICK(1)
-                win = block_argmax(gc, red_key, red_pos, red_row, rb);
-                TICK(2)
-                // (win.row < 0 cannot happen while jg < nsteps = min(n, v): some row is still active)
-                const int wcta = win.row / p.R;
-                if (t < nbc) {
-                    const uint2* wr = p.slot_rows + (size_t)(par * MAXG + wcta) * 64 + 2 * t;
-                    uint4 a;
-                    do {
-                        a = ld_ll2(wr);
-                    } while (a.y != epoch || a.w != epoch);
-                    const double x = __longlong_as_double((long long)(((unsigned long long)a.z << 32) | a.x));
-                    prow[t] = x;
-                    LU11[j * (NB + 1) + t] = x;
-                }
-
                 pr = prow;
+            }
+            if constexpr (!CLUSTER) {
+                __syncthreads();
+                win.key = 0;
+                win.pos = win_sh[0];
+                win.row = win_sh[1];
             }
             if (t == 0) {
                 pivrow_blk[j] = win.row;
                 if (cta == 0) p.perm_out[jg] = win.row;
             }
-            if constexpr (!CLUSTER) __syncthreads();
             TICK(3)
             const double pivot = pr[j];
             const double rinv = pivot != 0.0 ? 1.0 / pivot : 0.0;
@@ -355,9 +367,23 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                 for (int i = 0; i < NB; ++i) l[i] = (i < nsb) ? Ab[i * Rpad + lr] : 0.0;
                 double* wp = W + (int64_t)cstart * ldw + row_base + lr;
                 int cc = 0;
-                for (; cc + 3 < rem; cc += 4) {  // 4 independent global loads in flight, U12 read as 2 x LDS.128
-                    double w0 = wp[(int64_t)cc * ldw], w1 = wp[(int64_t)(cc + 1) * ldw];
-                    double w2 = wp[(int64_t)(cc + 2) * ldw], w3 = wp[(int64_t)(cc + 3) * ldw];
+                // 4 columns per iteration, software-pipelined: the loads of the next 4 columns are issued before the
+                // FMAs of the current ones (4 warps per SM cannot hide an L2 round trip otherwise); U12 as 2 x LDS.128
+                double w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+                if (rem >= 4) {
+                    w0 = wp[0];
+                    w1 = wp[ldw];
+                    w2 = wp[2 * ldw];
+                    w3 = wp[3 * ldw];
+                }
+                for (; cc + 3 < rem; cc += 4) {
+                    double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+                    if (cc + 7 < rem) {
+                        n0 = wp[(int64_t)(cc + 4) * ldw];
+                        n1 = wp[(int64_t)(cc + 5) * ldw];
+                        n2 = wp[(int64_t)(cc + 6) * ldw];
+                        n3 = wp[(int64_t)(cc + 7) * ldw];
+                    }
 #pragma unroll
                     for (int i = 0; i < NB; ++i) {
                         const double2 ua = *reinterpret_cast<const double2*>(U12 + i * v + cc);
@@ -371,6 +397,10 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                     wp[(int64_t)(cc + 1) * ldw] = w1;
                     wp[(int64_t)(cc + 2) * ldw] = w2;
                     wp[(int64_t)(cc + 3) * ldw] = w3;
+                    w0 = n0;
+                    w1 = n1;
+                    w2 = n2;
+                    w3 = n3;
                 }
                 for (; cc < rem; ++cc) {
                     double w0 = wp[(int64_t)cc * ldw];
@@ -396,7 +426,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
 template <int NB>
 size_t panel_smem_bytes(int Rpad, int v) {
     return ((size_t)NB * Rpad + (size_t)NB * v + NB * (NB + 1) + NB) * sizeof(double) +
-           2 * PT_WARPS * (sizeof(unsigned long long) + 2 * sizeof(int)) + (NB + 2) * sizeof(int) +
+           2 * PT_WARPS * (sizeof(unsigned long long) + 2 * sizeof(int)) + (NB + 4) * sizeof(int) +
            2 * CS_MAX * (NB + 2) * sizeof(unsigned long long) + 64;
 }
 
