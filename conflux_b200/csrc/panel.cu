@@ -28,7 +28,7 @@
 namespace cflx {
 
 namespace {
-constexpr int PT_THREADS = 128;
+constexpr int PT_THREADS = 256;  // 8 warps: two per scheduler, so dependent DFMA/LDS chains of one warp are covered
 constexpr int PT_WARPS = PT_THREADS / 32;
 constexpr int MAXG = 148;
 constexpr int RPT_LIMIT = 8;  // rows per thread -> R <= 1024 rows per CTA
@@ -231,11 +231,12 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                     st_ll(myrow, (unsigned)x, epoch);
                     st_ll(myrow + 1, (unsigned)(x >> 32), epoch);
                 }
-                // warp 0 alone gathers every CTA's candidate, picks the winner (warp-level argmax, no block barrier) and
-                // fetches the winner's inner-block row; the other warps wait at the single barrier below
-                if (t < 32) {
+                // warp 0 alone gathers every CTA's candidate (G <= 32: one slot per lane), picks the winner with a
+                // warp-level argmax (no block barrier) and fetches the winner's inner-block row; the other warps wait
+                // at the single barrier below.  Larger grids poll with all warps and reduce block-wide.
+                if (p.G > 32) {
                     Cand gc{0ull, INT_MAX, -1};
-                    for (int g = t; g < p.G; g += 32) {
+                    for (int g = t; g < p.G; g += PT_THREADS) {
                         const uint2* h = p.slot_hdr + (size_t)(par * MAXG + g) * 4;
                         uint4 a, b;
                         do {
@@ -244,6 +245,35 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                         } while (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch);
                         Cand o{((unsigned long long)a.z << 32) | a.x, (int)b.x, (int)b.z};
                         if (better(o, gc)) gc = o;
+                    }
+                    TICK(1)
+                    const Cand w = block_argmax(gc, red_key, red_pos, red_row, rb);
+                    TICK(2)
+                    const int wcta = w.row / p.R;
+                    if (t < nbc) {
+                        const uint2* wr = p.slot_rows + (size_t)(par * MAXG + wcta) * 64 + 2 * t;
+                        uint4 a;
+                        do {
+                            a = ld_ll2(wr);
+                        } while (a.y != epoch || a.w != epoch);
+                        const double x = __longlong_as_double((long long)(((unsigned long long)a.z << 32) | a.x));
+                        prow[t] = x;
+                        LU11[j * (NB + 1) + t] = x;
+                    }
+                    if (t == 0) {
+                        win_sh[0] = w.pos;
+                        win_sh[1] = w.row;
+                    }
+                } else if (t < 32) {
+                    Cand gc{0ull, INT_MAX, -1};
+                    if (t < p.G) {
+                        const uint2* h = p.slot_hdr + (size_t)(par * MAXG + t) * 4;
+                        uint4 a, b;
+                        do {
+                            a = ld_ll2(h);
+                            b = ld_ll2(h + 2);
+                        } while (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch);
+                        gc = Cand{((unsigned long long)a.z << 32) | a.x, (int)b.x, (int)b.z};
                     }
                     TICK(1)
                     const Cand w = warp_argmax(gc);
