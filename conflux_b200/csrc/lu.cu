@@ -702,8 +702,8 @@ int cflx_lu_create(cflx_comm* c, int M, int N, int v, int Px, int Py, int Pz, cf
         // rest.  A rank never has NCCL work in flight on both streams: the side stream's collectives (k- and
         // i-communicator) sit between the fork after GEMM_next and the join before the next world broadcast.
         const char* e = getenv("CFLX_LOOKAHEAD");
-        const char* em = getenv("CFLX_LOOKAHEAD_MULTI");  // multi-rank grids: opt-in until validated on hardware
-        const bool want = (e ? atoi(e) != 0 : true) && (lu->P == 1 || (em && atoi(em) != 0));
+        const char* em = getenv("CFLX_LOOKAHEAD_MULTI");  // multi-rank grids: on by default (validated on 2x2x1 / 1x1x2)
+        const bool want = (e ? atoi(e) != 0 : true) && (lu->P == 1 || !em || atoi(em) != 0);
         if (want) {
             int lo = 0, hi = 0;
             cudaDeviceGetStreamPriorityRange(&lo, &hi);
