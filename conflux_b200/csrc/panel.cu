@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
     // cslot[parity][cta][0] = key, [1] = pos | row << 32, [2..2+NB) = the candidate's inner-block row
     int* win_sh = pivrow_blk + NB;  // [2] winner {pos, row} broadcast by warp 0 (grid mode)
     unsigned long long* cslot = reinterpret_cast<unsigned long long*>(pivrow_blk + NB + 2 + (NB & 1));
+    unsigned char* s_act = reinterpret_cast<unsigned char*>(cslot + 2 * CS_MAX * (NB + 2));  // [Rpad] row still active?
     int rb = 0;
 
     const int t = threadIdx.x;
@@ -155,18 +156,17 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
         active[q] = lr < Rloc;
         pib[q] = -1;
     }
+    for (int lr = t; lr < Rpad; lr += PT_THREADS) s_act[lr] = lr < Rloc ? 1 : 0;
 
     for (int jb = 0; jb < p.nsteps; jb += NB) {
         const int nbc = min(NB, v - jb);         // columns in this block
         const int nsb = min(nbc, p.nsteps - jb);  // elimination steps in this block
         // ---- phase A: load the inner block of my rows (coalesced rows of W) ----
-        for (int c = 0; c < nbc; ++c) {
-#pragma unroll
-            for (int q = 0; q < RPT_MAX; ++q) {
-                const int lr = t + q * PT_THREADS;
-                if (lr < Rloc) Ab[c * Rpad + lr] = W[(int64_t)(jb + c) * ldw + row_base + lr];
-            }
+        for (int e = t; e < nbc * Rpad; e += PT_THREADS) {  // all threads, coalesced along the rows of W
+            const int c = e / Rpad, lr = e - c * Rpad;
+            if (lr < Rloc) Ab[e] = W[(int64_t)(jb + c) * ldw + row_base + lr];
         }
+        __syncthreads();
         // (each thread touches only its own rows of Ab until a winner row is published after a block sync)
         TICK(5)
 
@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                 if (!active[q]) continue;
                 if (row_base + lr == win.row) {
                     active[q] = false;
+                    s_act[lr] = 0;
                     pib[q] = j;
                     continue;
                 }
@@ -344,12 +345,10 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
         }
 
         // ---- write the inner block back (L multipliers; pivot rows keep their LU row) ----
-        for (int c = 0; c < nbc; ++c) {
-#pragma unroll
-            for (int q = 0; q < RPT_MAX; ++q) {
-                const int lr = t + q * PT_THREADS;
-                if (lr < Rloc) W[(int64_t)(jb + c) * ldw + row_base + lr] = Ab[c * Rpad + lr];
-            }
+        __syncthreads();  // every row's inner block is final
+        for (int e = t; e < nbc * Rpad; e += PT_THREADS) {
+            const int c = e / Rpad, lr = e - c * Rpad;
+            if (lr < Rloc) W[(int64_t)(jb + c) * ldw + row_base + lr] = Ab[e];
         }
         if (cta == 0 && p.A00 != nullptr) {
             for (int e = t; e < nsb * nbc; e += PT_THREADS) {
@@ -388,31 +387,31 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
             }
             __syncthreads();
             TICK(6)
-#pragma unroll 1
-            for (int q = 0; q < RPT_MAX; ++q) {
-                const int lr = t + q * PT_THREADS;
-                if (lr >= Rloc || !active[q]) continue;  // finished pivot rows are never read again
+            // rank-NB update of my rows.  One thread per (row, column group): with R >= 256 rows per CTA a thread walks
+            // all trailing columns of its row(s); with fewer rows the PT_THREADS / R threads that share a row split the
+            // columns (groups of 4, interleaved), so small panels still use every thread of every CTA.
+            auto update_row = [&](int lr, int cfirst, int cstep, bool tail) {
                 double l[NB];
 #pragma unroll
                 for (int i = 0; i < NB; ++i) l[i] = (i < nsb) ? Ab[i * Rpad + lr] : 0.0;
                 double* wp = W + (int64_t)cstart * ldw + row_base + lr;
-                int cc = 0;
-                // 4 columns per iteration, software-pipelined: the loads of the next 4 columns are issued before the
-                // FMAs of the current ones (4 warps per SM cannot hide an L2 round trip otherwise); U12 as 2 x LDS.128
+                int cc = cfirst;
+                // software-pipelined: the loads of the next group are issued before the FMAs of the current one
                 double w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-                if (rem >= 4) {
-                    w0 = wp[0];
-                    w1 = wp[ldw];
-                    w2 = wp[2 * ldw];
-                    w3 = wp[3 * ldw];
+                if (cc + 3 < rem) {
+                    w0 = wp[(int64_t)cc * ldw];
+                    w1 = wp[(int64_t)(cc + 1) * ldw];
+                    w2 = wp[(int64_t)(cc + 2) * ldw];
+                    w3 = wp[(int64_t)(cc + 3) * ldw];
                 }
-                for (; cc + 3 < rem; cc += 4) {
+                for (; cc + 3 < rem; cc += cstep) {
                     double n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-                    if (cc + 7 < rem) {
-                        n0 = wp[(int64_t)(cc + 4) * ldw];
-                        n1 = wp[(int64_t)(cc + 5) * ldw];
-                        n2 = wp[(int64_t)(cc + 6) * ldw];
-                        n3 = wp[(int64_t)(cc + 7) * ldw];
+                    const int cn = cc + cstep;
+                    if (cn + 3 < rem) {
+                        n0 = wp[(int64_t)cn * ldw];
+                        n1 = wp[(int64_t)(cn + 1) * ldw];
+                        n2 = wp[(int64_t)(cn + 2) * ldw];
+                        n3 = wp[(int64_t)(cn + 3) * ldw];
                     }
 #pragma unroll
                     for (int i = 0; i < NB; ++i) {
@@ -432,11 +431,25 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                     w2 = n2;
                     w3 = n3;
                 }
-                for (; cc < rem; ++cc) {
-                    double w0 = wp[(int64_t)cc * ldw];
+                if (tail) {
+                    for (int ct = rem & ~3; ct < rem; ++ct) {
+                        double x = wp[(int64_t)ct * ldw];
 #pragma unroll
-                    for (int i = 0; i < NB; ++i) w0 -= l[i] * U12[i * v + cc];
-                    wp[(int64_t)cc * ldw] = w0;
+                        for (int i = 0; i < NB; ++i) x -= l[i] * U12[i * v + ct];
+                        wp[(int64_t)ct * ldw] = x;
+                    }
+                }
+            };
+            if (RPT_MAX == 1 && p.R < PT_THREADS) {
+                const int nshare = PT_THREADS / p.R;  // threads per row
+                const int lr = t % p.R, part = t / p.R;
+                if (part < nshare && lr < Rloc && s_act[lr]) update_row(lr, 4 * part, 4 * nshare, part == 0);
+            } else {
+#pragma unroll 1
+                for (int q = 0; q < RPT_MAX; ++q) {
+                    const int lr = t + q * PT_THREADS;
+                    if (lr >= Rloc || !active[q]) continue;  // finished pivot rows are never read again
+                    update_row(lr, 0, 4, true);
                 }
             }
         }
@@ -457,7 +470,7 @@ template <int NB>
 size_t panel_smem_bytes(int Rpad, int v) {
     return ((size_t)NB * Rpad + (size_t)NB * v + NB * (NB + 1) + NB) * sizeof(double) +
            2 * PT_WARPS * (sizeof(unsigned long long) + 2 * sizeof(int)) + (NB + 4) * sizeof(int) +
-           2 * CS_MAX * (NB + 2) * sizeof(unsigned long long) + 64;
+           2 * CS_MAX * (NB + 2) * sizeof(unsigned long long) + (size_t)Rpad + 64;
 }
 
 template <int NB, int RPT>
@@ -545,7 +558,9 @@ int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, 
         cluster_rows = e ? atoi(e) : 0;  // opt-in until validated on hardware
     }
     const bool cluster = (n <= cluster_rows) && (n <= CS_MAX * RPT_LIMIT * PT_THREADS);
-    int G = (n + PT_THREADS - 1) / PT_THREADS;
+    // as many CTAs as the cap allows down to 32 rows per CTA: small panels (late steps, tournament stacks) are spread
+    // over up to 32 SMs and the threads that share a row split the trailing columns in phase C
+    int G = (n + 31) / 32;
     if (G < 1) G = 1;
     if (G > ws->max_ctas) G = ws->max_ctas;
     if (ws->cta_cap > 0 && G > ws->cta_cap) G = ws->cta_cap;
