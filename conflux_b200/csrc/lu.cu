@@ -104,7 +104,7 @@ struct cflx_lu {
     std::vector<cudaEvent_t> ev;
     std::vector<char> ev_used;
     cudaStream_t side = nullptr;  // high-priority look-ahead stream (null: no overlap)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_npiv = nullptr;
 };
 
 namespace {
@@ -353,69 +353,40 @@ int finish_step(cflx_lu* lu, int k, int& fnpr) {
         lu->launches++;
     }
     // ---- step 2: localise pivots, push them up, extract pivot rows        conflux_opt.hpp:876-1147
-    int npiv = v;
+    // At Px > 1 the host needs this rank's pivot count (it sizes the L-panel work).  Everything that does NOT depend
+    // on it -- row moves, pivot-row reduce, the U solve, its broadcast, the factor stores -- is enqueued first, and
+    // the host only then waits for the 4-byte read-back, so the GPU stays busy while the rest is enqueued.
     {
         PhaseTimer t(lu, PH_MOVES);
         CFLX_TRY(launch_plan_moves(lu->gpivots, v, Px, pi, fnpr_old, Ml, lu->igri, lu->plan, s));
         lu->launches++;
         if (Px > 1) {
             CFLX_CUDA(cudaMemcpyAsync(lu->h_npiv, lu->plan.npiv, sizeof(int), cudaMemcpyDeviceToHost, s));
-            CFLX_CUDA(cudaStreamSynchronize(s));
-            npiv = *lu->h_npiv;
-        }
-        if (npiv < 0 || npiv > v || fnpr_old + npiv > Ml) {
-            set_last_error("step %d: inconsistent pivot count %d (fnpr %d, Ml %d)", k, npiv, fnpr_old, Ml);
-            return CFLX_ERR_STATE;
+            CFLX_CUDA(cudaEventRecord(lu->ev_npiv, s));
         }
         const int col_lo = layer0 ? 0 : loff;
-        const int64_t ldu = std::max(2, ncols);
-        if (ncols > 0 || npiv > 0) {
-            CFLX_TRY(launch_push_phase1(lu->A11, Nl, Nl, col_lo, lu->plan, v, lu->tmp, ncols > 0 ? lu->A01raw : nullptr, ldu,
-                                        c0, s));
-            CFLX_TRY(launch_push_phase2(lu->A11, Nl, Nl, col_lo, lu->plan, v, s));
-            CFLX_TRY(launch_push_phase3(lu->A11, Nl, Nl, col_lo, fnpr_old, lu->plan, v, lu->tmp, s));
-            lu->launches += 3;
-        }
+        const int64_t ldu0 = std::max(2, ncols);
+        CFLX_TRY(launch_push_phase1(lu->A11, Nl, Nl, col_lo, lu->plan, v, lu->tmp, ncols > 0 ? lu->A01raw : nullptr, ldu0, c0,
+                                    s));
+        CFLX_TRY(launch_push_phase2(lu->A11, Nl, Nl, col_lo, lu->plan, v, s));
+        CFLX_TRY(launch_push_phase3(lu->A11, Nl, Nl, col_lo, fnpr_old, lu->plan, v, lu->tmp, s));
         CFLX_TRY(launch_update_gri(lu->gri, lu->gri_tmp, lu->igri, lu->plan.rowsrc, fnpr_old, Ml, v, Px, s));
-        lu->launches += 2;
+        lu->launches += 5;
     }
-    fnpr = fnpr_old + npiv;
-    const int n_act = Ml - fnpr;
-    const int64_t ld2 = std::max<int64_t>(2, round_up(n_act, 2));
     const int64_t ldu = std::max(2, ncols);
     // At Px == 1 the local pivot search IS the panel factorisation: its multipliers are the L panel (same values a
     // LAPACK getrf leaves behind; the reference recomputes them with dtrsm against A00, conflux_opt.hpp:1347).
     const bool fused_l = (nR == 0);
-    if (on_col && layer0 && n_act > 0) {
-        PhaseTimer t(lu, PH_MOVES);
-        CFLX_TRY(launch_compact_panel(fused_l ? lu->W : lu->PT, ldk, fused_l ? lu->LT : lu->PT2, ld2, lu->plan.rowsrc,
-                                      fnpr_old, lu->plan.npiv, Ml, v, s));
-        lu->launches++;
-    }
     // ---- steps 2b/3: pivot rows summed over layers and gathered on row pi == k % Px   conflux_opt.hpp:1164-1260
     if (ncols > 0 && Px * Pz > 1) {
         PhaseTimer t(lu, PH_REDUCE);
         CFLX_NCCL(ncclReduce(lu->A01raw, lu->A01raw, (size_t)v * ldu, ncclDouble, ncclSum, pik * Pz, lu->ik_comm.c, s));
     }
-    // ---- steps 4/5: the two triangular solves                              conflux_opt.hpp:1329-1359,1522-1551
+    // ---- step 5 first: U = L00^-1 * (pivot rows)                            conflux_opt.hpp:1522-1593
     if (layer0 && ((on_col && !fused_l) || on_row)) {
         PhaseTimer t(lu, PH_TRSM);
         CFLX_TRY(launch_diag_inverses(A00, v, lu->nb, lu->Uinv, lu->LinvT, s));
         lu->launches++;
-    }
-    if (on_col && layer0 && n_act > 0) {
-        if (!fused_l) {
-            PhaseTimer t(lu, PH_TRSM);
-            CFLX_TRY(trsm_right_upper_T(A00, lu->Uinv, v, lu->nb, lu->PT2, lu->LT, ld2, n_act, s));
-            lu->launches += 2 * (v / lu->nb) - 1;
-        }
-        PhaseTimer t(lu, PH_STORE);
-        CFLX_TRY(launch_store_panel_T(lu->A11, Nl, fnpr, loff, n_act, v, lu->LT, ld2, s));  // L in place
-        lu->launches++;
-    }
-    if (Py * Pz > 1 && n_act > 0) {  // L panel to every (pj', pk') of my grid row    conflux_opt.hpp:1404-1434
-        PhaseTimer t(lu, PH_REDUCE);
-        CFLX_NCCL(ncclBroadcast(lu->LT, lu->LT, (size_t)v * ld2, ncclDouble, pjk * Pz, lu->jk_comm.c, s));
     }
     // The U solve is split in two column windows: the first v columns (= the next panel) are solved before the
     // look-ahead fork, the rest after it, off the pivot search's critical path (single-rank grids only: with more
@@ -445,6 +416,40 @@ int finish_step(cflx_lu* lu, int k, int& fnpr) {
         return CFLX_OK;
     };
     if (!split_u) CFLX_TRY(store_factors());
+    // ---- now the pivot count: sizes of the L panel and of the trailing update
+    int npiv = v;
+    if (Px > 1) {
+        CFLX_CUDA(cudaEventSynchronize(lu->ev_npiv));
+        npiv = *lu->h_npiv;
+    }
+    if (npiv < 0 || npiv > v || fnpr_old + npiv > Ml) {
+        set_last_error("step %d: inconsistent pivot count %d (fnpr %d, Ml %d)", k, npiv, fnpr_old, Ml);
+        return CFLX_ERR_STATE;
+    }
+    fnpr = fnpr_old + npiv;
+    const int n_act = Ml - fnpr;
+    const int64_t ld2 = std::max<int64_t>(2, round_up(n_act, 2));
+    // ---- step 4: L = A10 * U00^-1 on the panel column                       conflux_opt.hpp:1329-1434
+    if (on_col && layer0 && n_act > 0) {
+        {
+            PhaseTimer t(lu, PH_MOVES);
+            CFLX_TRY(launch_compact_panel(fused_l ? lu->W : lu->PT, ldk, fused_l ? lu->LT : lu->PT2, ld2, lu->plan.rowsrc,
+                                          fnpr_old, lu->plan.npiv, Ml, v, s));
+            lu->launches++;
+        }
+        if (!fused_l) {
+            PhaseTimer t(lu, PH_TRSM);
+            CFLX_TRY(trsm_right_upper_T(A00, lu->Uinv, v, lu->nb, lu->PT2, lu->LT, ld2, n_act, s));
+            lu->launches += 2 * (v / lu->nb) - 1;
+        }
+        PhaseTimer t(lu, PH_STORE);
+        CFLX_TRY(launch_store_panel_T(lu->A11, Nl, fnpr, loff, n_act, v, lu->LT, ld2, s));  // L in place
+        lu->launches++;
+    }
+    if (Py * Pz > 1 && n_act > 0) {  // L panel to every (pj', pk') of my grid row    conflux_opt.hpp:1404-1434
+        PhaseTimer t(lu, PH_REDUCE);
+        CFLX_NCCL(ncclBroadcast(lu->LT, lu->LT, (size_t)v * ld2, ncclDouble, pjk * Pz, lu->jk_comm.c, s));
+    }
     // ---- step 6: trailing update on every rank and layer                    conflux_opt.hpp:1628-1632
     // Look-ahead: the rank that owns panel k+1 updates those v columns first (they are its first live block), forks
     // the pivot search of iteration k+1 onto the side stream, and only then updates the remaining columns.
@@ -496,6 +501,7 @@ void free_lu(cflx_lu* lu) {
     if (lu->side) cudaStreamDestroy(lu->side);
     if (lu->ev_fork) cudaEventDestroy(lu->ev_fork);
     if (lu->ev_join) cudaEventDestroy(lu->ev_join);
+    if (lu->ev_npiv) cudaEventDestroy(lu->ev_npiv);
     for (SubComm* sc : {&lu->k_comm, &lu->i_comm, &lu->jk_comm, &lu->ik_comm})
         if (sc->c) ncclCommDestroy(sc->c);
     delete lu;
@@ -693,6 +699,7 @@ int cflx_lu_create(cflx_comm* c, int M, int N, int v, int Px, int Py, int Pz, cf
     pm += v;
     lu->plan.rowsrc = pm;
     if (cudaMallocHost((void**)&lu->h_npiv, sizeof(int)) != cudaSuccess) return fail(CFLX_ERR_CUDA);
+    if (cudaEventCreateWithFlags(&lu->ev_npiv, cudaEventDisableTiming) != cudaSuccess) return fail(CFLX_ERR_CUDA);
     if ((rc = panel_workspace_create(&lu->pws))) return fail(rc);
     if ((rc = gemm_tn_setup())) return fail(rc);
     lu->h_hist.assign(lu->M, -1);
