@@ -266,7 +266,11 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tn_kernel (trailing update, DMMA.8x8x4)",
                          "achieved": g_tf, "peak": dmma_peak, "unit": "TFLOP/s", "frac": (g_tf / dmma_peak) if g_tf else None,
-                         "traffic": None,
+                         # dram__bytes_read+write of ONE launch from the committed `ncu --set full` capture of the
+                         # first-step shape (M=N=16128, K=256; profiles/r01_gemm_full.md): 2.798 + 2.058 GB, against
+                         # 16*M*N + 8*K*(M+N) = 4.228 GB algorithmic (C read+write once, operands once)
+                         "traffic": 4.856e9 if not override and args.gpus == 1 else None,
+                         "traffic_launch": "M=N=16128 K=256 (step 0), algorithmic 4.228e9 B, ncu capture profiles/r01_gemm_full.md",
                          "peak_sustained": peak_sustained,
                          "peak_source": "FP64 tensor (DMMA.8x8x4) peak measured live on this GPU by cflx_dbg_fp64_peak_ex: `peak` = burst "
                                         "(best ~2 ms launch), `peak_sustained` = one 0.5 s launch under the power cap; "
