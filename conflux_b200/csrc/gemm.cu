@@ -32,6 +32,16 @@ struct Cfg {
     static constexpr size_t SMEM = (size_t)STAGES * BK * (LDA + LDB) * sizeof(double) + 2 * STAGES * sizeof(uint64_t);
 };
 
+// C may alias D (the trailing update is in place), so the read-only (.nc) path is off limits.  A plain coherent 16-byte
+// load, written as non-volatile asm without a memory clobber: the compiler may schedule it freely among the stores of
+// OTHER elements (each element is read exactly once, by the thread that later writes it; the data dependence keeps
+// that load ahead of its own store), which preserves the batched-load memory-level parallelism.
+__device__ __forceinline__ double2 ld_c2(const double* p) {
+    double2 v;
+    asm("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
 template <int WM, int WN, int MINB>
 __global__ void __launch_bounds__(Cfg<WM, WN>::NTHREADS, MINB) gemm_tn_kernel(GemmArgs g) {
     using C = Cfg<WM, WN>;
@@ -128,7 +138,7 @@ __global__ void __launch_bounds__(Cfg<WM, WN>::NTHREADS, MINB) gemm_tn_kernel(Ge
                 const int col = n0 + wn_off + 8 * j + 2 * t4;
                 cv[ii][j] = make_double2(0.0, 0.0);
                 if (use_c && row < g.M && col < g.N)
-                    cv[ii][j] = __ldg(reinterpret_cast<const double2*>(g.C + (int64_t)row * g.ldc + col));
+                    cv[ii][j] = ld_c2(g.C + (int64_t)row * g.ldc + col);
             }
         }
 #pragma unroll

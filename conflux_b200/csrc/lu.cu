@@ -166,23 +166,29 @@ int tournament_exchange(cflx_lu* lu, int r, int my_half, cudaStream_t s) {
     double* recv = lu->candH + other * hv;
     int* mine_t = lu->tagsH + my_half * v;
     int* recv_t = lu->tagsH + other * v;
-    if (src == pi) {  // MPI_Sendrecv with itself: the own half is duplicated into the other half
+    const bool self = (src == pi);
+    if (self) {  // MPI_Sendrecv with itself: the own half is duplicated into the other half (conflux_opt.hpp:258-266)
         CFLX_CUDA(cudaMemcpyAsync(recv, mine, hv * sizeof(double), cudaMemcpyDeviceToDevice, s));
         CFLX_CUDA(cudaMemcpyAsync(recv_t, mine_t, v * sizeof(int), cudaMemcpyDeviceToDevice, s));
-        return CFLX_OK;
     }
+    // a self-paired rank still serves one-sided requesters (the reference's extra Isend, conflux_opt.hpp:271-279)
+    bool any = !self;
+    for (int ppi = 0; ppi < Px && !any; ++ppi) any = (ppi != pi && butterfly_pair(ppi, r, Px) == pi);
+    if (!any) return CFLX_OK;
     CFLX_NCCL(ncclGroupStart());
     for (int ppi = 0; ppi < Px; ++ppi) {
         if (ppi == pi || butterfly_pair(ppi, r, Px) != pi) continue;
-        // mutual partner gets my own half; a one-sided requester gets the lower half (the reference's extra Isend)
-        const bool mutual = (ppi == src);
+        // mutual partner gets my own half; a one-sided requester gets the lower half
+        const bool mutual = (!self && ppi == src);
         const double* sv = mutual ? mine : lu->candH + hv;
         const int* st = mutual ? mine_t : lu->tagsH + v;
         CFLX_NCCL(ncclSend(sv, hv, ncclDouble, ppi, lu->i_comm.c, s));
         CFLX_NCCL(ncclSend(st, v, ncclInt, ppi, lu->i_comm.c, s));
     }
-    CFLX_NCCL(ncclRecv(recv, hv, ncclDouble, src, lu->i_comm.c, s));
-    CFLX_NCCL(ncclRecv(recv_t, v, ncclInt, src, lu->i_comm.c, s));
+    if (!self) {
+        CFLX_NCCL(ncclRecv(recv, hv, ncclDouble, src, lu->i_comm.c, s));
+        CFLX_NCCL(ncclRecv(recv_t, v, ncclInt, src, lu->i_comm.c, s));
+    }
     CFLX_NCCL(ncclGroupEnd());
     return CFLX_OK;
 }

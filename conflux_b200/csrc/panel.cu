@@ -12,8 +12,11 @@
 //     swapped order) is reproduced exactly (needed for the reference's integer test matrices);
 //   * right-looking with an NB-column inner block held in shared memory; per column ONE grid-wide exchange:
 //     every CTA publishes its best candidate together with that row's inner-block values into a double-buffered
-//     global slot (st.release.gpu), then reads all slots (ld.acquire.gpu) and picks the winner redundantly --
-//     no second round trip for the pivot row, no grid barrier;
+//     global slot as "LL" words (payload + epoch in one 8-byte volatile store: the flag travels with the data), then
+//     polls all slots and picks the winner redundantly -- no second round trip for the pivot row, no grid barrier.
+//     The LL words order only their own payload; the trailing columns of W that phase C writes with plain stores and
+//     that OTHER CTAs gather as pivot rows one block later are ordered by a gpu-scope fence pair per NB-column block
+//     (writer: __threadfence() after the phase-C write-back; reader: __threadfence() before the U12 gathers);
 //   * warp-level argmax with redux.sync on the (hi, lo) words of |a| and the position;
 //   * after NB columns each CTA redundantly solves U12 = L11^-1 A12 (NB x rem, shared memory) and applies the
 //     rank-NB update to its own rows with the multipliers in registers; CTA 0 emits the rows of L00\U00.
@@ -220,6 +223,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                 // publish my CTA's candidate and its inner-block row (LL words, fire and forget)
                 const unsigned epoch = (unsigned)(p.epoch_base + jg + 1);
                 uint2* myhdr = p.slot_hdr + (size_t)(par * MAXG + cta) * 4;
+                if (j == 0 && t < 32) __threadfence();  // publisher-side half of the per-block release (cumulative)
                 if (t < 4) {
                     const unsigned w = t == 0 ? (unsigned)mine.key : t == 1 ? (unsigned)(mine.key >> 32)
                                      : t == 2 ? (unsigned)mine.pos : (unsigned)mine.row;
@@ -363,6 +367,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
         const int rem = v - cstart;
         if (rem > 0) {
             __syncthreads();  // pivrow_blk, LU11 complete
+            __threadfence();  // acquire: the epochs observed in phase B order the owners' earlier W stores before my gathers
             // one trailing column per thread: NB independent scattered loads in flight, then the unit-lower forward
             // substitution entirely in registers (L11 broadcast from shared memory)
             for (int cc = t; cc < rem; cc += PT_THREADS) {
@@ -455,6 +460,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
         }
 #pragma unroll
         for (int q = 0; q < RPT_MAX; ++q) pib[q] = -1;
+        // release: my phase-C stores to W must be visible gpu-wide before any LL word of the NEXT block is published
+        // (other CTAs gather these rows as pivot rows after observing that block's epochs)
+        __threadfence();
         __syncthreads();  // Ab / U12 / LU11 are rewritten by the next block
         TICK(7)
     }
@@ -563,13 +571,19 @@ int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, 
     int G = (n + 31) / 32;
     if (G < 1) G = 1;
     if (G > ws->max_ctas) G = ws->max_ctas;
-    if (ws->cta_cap > 0 && G > ws->cta_cap) G = ws->cta_cap;
+    if (ws->cta_cap > 0 && G > ws->cta_cap) {
+        G = ws->cta_cap;
+        // the look-ahead cap must not shrink the row capacity below the panel: widen the grid again when needed
+        const int need = (n + RPT_LIMIT * PT_THREADS - 1) / (RPT_LIMIT * PT_THREADS);
+        if (G < need) G = need < ws->max_ctas ? need : ws->max_ctas;
+    }
     if (cluster && G > CS_MAX) G = CS_MAX;
     int R = (n + G - 1) / G;
     R = (int)round_up(R > 0 ? R : 1, 32);
     G = n > 0 ? (n + R - 1) / R : 1;
     if (R > RPT_LIMIT * PT_THREADS) {
-        set_last_error("panel_getrf: n=%d rows exceed the %d-row capacity", n, ws->max_ctas * RPT_LIMIT * PT_THREADS);
+        set_last_error("panel_getrf: n=%d rows exceed the %d-row capacity (%d CTAs x %d rows)", n,
+                       ws->max_ctas * RPT_LIMIT * PT_THREADS, ws->max_ctas, RPT_LIMIT * PT_THREADS);
         return CFLX_ERR_UNSUPPORTED;
     }
     a.R = R;
@@ -586,6 +600,12 @@ int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, 
     int nb = v >= 32 ? 32 : (v >= 16 ? 16 : (v >= 8 ? 8 : 4));
     if (nb == 32 && panel_smem_bytes<32>(a.Rpad, v) > budget) nb = 16;
     if (nb == 16 && panel_smem_bytes<16>(a.Rpad, v) > budget) nb = 8;
+    if (nb == 8 && panel_smem_bytes<8>(a.Rpad, v) > budget) nb = 4;
+    if (nb == 4 && panel_smem_bytes<4>(a.Rpad, v) > budget) {
+        set_last_error("panel_getrf: v=%d with %d rows per CTA needs %zu B of shared memory (budget %zu)", v, a.Rpad,
+                       panel_smem_bytes<4>(a.Rpad, v), budget);
+        return CFLX_ERR_UNSUPPORTED;
+    }
     if (nb_used) *nb_used = nb;
     switch (nb) {
         case 32: return launch_nb<32>(a, cluster, stream);
