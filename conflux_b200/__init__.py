@@ -15,7 +15,7 @@ import numpy as np
 
 from ._lib import ConfluxError, LIB_PATH, SYMBOLS, check, lib
 
-__all__ = ["pinned_empty", "pinned_free", "Comm", "lu_params", "LU_rep", "residual", "auto_grid", "lu_dims", "init_matrix_host", "ConfluxError", "dbg"]
+__all__ = ["pinned_empty", "pinned_free", "Comm", "lu_params", "LU_rep", "residual", "validate", "auto_grid", "lu_dims", "init_matrix_host", "ConfluxError", "dbg"]
 
 
 def auto_grid(M, N, P):
@@ -171,11 +171,17 @@ def LU_rep(gv, C=None, permutation=None, upload=True):
     return ms.value
 
 
+def validate(gv):
+    """The reference's validation (examples/conflux_miniapp.cpp:349-500) of the last LU_rep on the GPU grid.
+    COLLECTIVE over gv.lu_comm.  Returns (||PA - LU||_F, ||PA - LU||_F / ||A||_F), identical on every rank."""
+    a, r = ctypes.c_double(), ctypes.c_double()
+    check(lib().cflx_lu_validate(gv._h, ctypes.byref(a), ctypes.byref(r)), "lu_validate")
+    return a.value, r.value
+
+
 def residual(gv):
-    """||PA - LU||_F / ||A||_F of the last LU_rep, computed on the GPU (single-rank grids)."""
-    r = ctypes.c_double()
-    check(lib().cflx_lu_residual(gv._h, ctypes.byref(r)), "lu_residual")
-    return r.value
+    """||PA - LU||_F / ||A||_F of the last LU_rep, computed on the GPU grid (collective)."""
+    return validate(gv)[1]
 
 
 class dbg:
@@ -225,6 +231,17 @@ class dbg:
                                   X.ctypes.data if X is not None else None, R.ctypes.data if R is not None else None,
                                   Y.ctypes.data if Y is not None else None), "dbg_trsm")
         return X, Y
+
+    @staticmethod
+    def push_pivots(A, pivot_rows, fnpr):
+        """plan_moves + push_phase1..3 + gri update on one rank; returns (A_new, new_row -> old_row, extracted rows)."""
+        A = np.array(A, dtype=np.float64, order="C")
+        piv = np.ascontiguousarray(pivot_rows, dtype=np.int32)
+        gri = np.zeros(A.shape[0], dtype=np.int32)
+        a01 = np.zeros((max(1, len(piv)), A.shape[1]))
+        check(lib().cflx_dbg_push_pivots(A.shape[0], A.shape[1], A.ctypes.data, len(piv), piv.ctypes.data, int(fnpr),
+                                         gri.ctypes.data, a01.ctypes.data), "dbg_push_pivots")
+        return A, gri, a01[:len(piv)]
 
     @staticmethod
     def fp64_peak_ex(which):

@@ -253,4 +253,52 @@ int cflx_dbg_trsm(int n, int v, const double* A00, const double* B, double* X_ou
     return CFLX_OK;
 }
 
+// step 2 of the LU loop in isolation on ONE rank (Px = 1): plan_moves (analyze_pivots) + push_phase1..3 (push_pivots_up,
+// conflux_opt.hpp:176-218) + the gri/igri bookkeeping, on an n_rows x n_cols row-major matrix (n_cols even).  The npiv
+// pivot rows (local indices >= fnpr, tournament order) end up in rows [fnpr, fnpr+npiv) in that order.
+// gri_out[n_rows] (optional) = new row -> old row.  a01_out (optional, npiv x n_cols) = the pivot rows phase 1 extracts.
+int cflx_dbg_push_pivots(int n_rows, int n_cols, double* A_inout, int npiv, const int* pivot_rows, int fnpr, int* gri_out,
+                         double* a01_out) {
+    CFLX_TRY(check_device());
+    if (n_rows <= 0 || n_cols <= 0 || (n_cols & 1) || npiv < 0 || npiv > n_rows - fnpr || fnpr < 0) return CFLX_ERR_ARG;
+    if (npiv == 0) {
+        if (gri_out) for (int i = 0; i < n_rows; ++i) gri_out[i] = i;
+        return CFLX_OK;
+    }
+    const int v = npiv;  // every pivot of the "tile" lives on this rank
+    DevBuf dA, dtmp, da01, dplan, dgp, dgri, dgrit, digri;
+    CFLX_TRY(dA.alloc(8 * (size_t)n_rows * n_cols));
+    CFLX_TRY(dtmp.alloc(8 * (size_t)v * n_cols));
+    CFLX_TRY(da01.alloc(8 * (size_t)v * n_cols));
+    CFLX_TRY(dplan.alloc(sizeof(int) * (6 * (size_t)v + 8 + n_rows)));
+    CFLX_TRY(dgp.alloc(sizeof(int) * v));
+    CFLX_TRY(dgri.alloc(sizeof(int) * n_rows));
+    CFLX_TRY(dgrit.alloc(sizeof(int) * n_rows));
+    CFLX_TRY(digri.alloc(sizeof(int) * n_rows));
+    CFLX_CUDA(cudaMemcpy(dA.p, A_inout, 8 * (size_t)n_rows * n_cols, cudaMemcpyHostToDevice));
+    CFLX_CUDA(cudaMemcpy(dgp.p, pivot_rows, sizeof(int) * v, cudaMemcpyHostToDevice));
+    MovePlan plan{};
+    int* pm = dplan.as<int>();
+    plan.npiv = pm; plan.nel = pm + 4; pm += 8;
+    plan.cur_piv = pm; pm += v;
+    plan.order = pm; pm += v;
+    plan.slot2piv = pm; pm += v;
+    plan.early = pm; pm += v;
+    plan.late = pm; pm += 2 * v;
+    plan.rowsrc = pm;
+    // gri = identity with "tile size" n_rows so that global id == local row (Px = 1)
+    CFLX_TRY(launch_iota_gri(dgri.as<int>(), digri.as<int>(), n_rows, n_rows, 1, 0, 0));
+    // plan_moves maps a global id g to the local slot (g / (v*Px))*v + g % v: with v := n_rows that is g itself
+    CFLX_TRY(launch_plan_moves(dgp.as<int>(), v, 1, 0, fnpr, n_rows, digri.as<int>(), plan, 0));
+    CFLX_TRY(launch_push_phase1(dA.as<double>(), n_cols, n_cols, 0, plan, v, dtmp.as<double>(), da01.as<double>(), n_cols, 0, 0));
+    CFLX_TRY(launch_push_phase2(dA.as<double>(), n_cols, n_cols, 0, plan, v, 0));
+    CFLX_TRY(launch_push_phase3(dA.as<double>(), n_cols, n_cols, 0, fnpr, plan, v, dtmp.as<double>(), 0));
+    CFLX_TRY(launch_update_gri(dgri.as<int>(), dgrit.as<int>(), digri.as<int>(), plan.rowsrc, fnpr, n_rows, n_rows, 1, 0));
+    CFLX_CUDA(cudaMemcpy(A_inout, dA.p, 8 * (size_t)n_rows * n_cols, cudaMemcpyDeviceToHost));
+    if (gri_out) CFLX_CUDA(cudaMemcpy(gri_out, dgri.p, sizeof(int) * n_rows, cudaMemcpyDeviceToHost));
+    if (a01_out) CFLX_CUDA(cudaMemcpy(a01_out, da01.p, 8 * (size_t)v * n_cols, cudaMemcpyDeviceToHost));
+    CFLX_CUDA(cudaDeviceSynchronize());
+    return CFLX_OK;
+}
+
 }  // extern "C"

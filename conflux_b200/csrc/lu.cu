@@ -12,8 +12,6 @@
 //     (conflux_opt.hpp:818-850,872);
 //   * all communication is NCCL on the rank's stream; at Px == 1 the whole factorisation is enqueued without a
 //     single host synchronisation, at Px > 1 the host reads back one int (this rank's pivot count) per step.
-#include <nccl.h>
-
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -22,9 +20,7 @@
 #include <random>
 #include <vector>
 
-#include "../../include/conflux_b200.h"
-#include "common.cuh"
-#include "kernels.h"
+#include "lu_state.h"
 
 namespace cflx {
 static thread_local char g_err[1024] = "";
@@ -38,30 +34,7 @@ void set_last_error(const char* fmt, ...) {
 
 using namespace cflx;
 
-#define CFLX_NCCL(call)                                                                            \
-    do {                                                                                           \
-        ncclResult_t r__ = (call);                                                                 \
-        if (r__ != ncclSuccess) {                                                                  \
-            set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(r__)); \
-            return CFLX_ERR_NCCL;                                                                  \
-        }                                                                                          \
-    } while (0)
-
-struct cflx_comm {
-    int world_size = 1, world_rank = 0, device = 0;
-    ncclComm_t world = nullptr;
-    cudaStream_t stream = nullptr;
-    double* d_scratch = nullptr;  // 1 double for barriers
-};
-
 namespace {
-struct SubComm {
-    ncclComm_t c = nullptr;
-    int size = 1, rank = 0;
-};
-
-enum Phase { PH_PANEL = 0, PH_TOURN, PH_MOVES, PH_REDUCE, PH_TRSM, PH_GEMM, PH_STORE, PH_OTHER, PH_COUNT };
-
 int flipbit(int n, int k) { return n ^ (1 << k); }
 int butterfly_pair(int pi, int r, int Px) {  // conflux_opt.cpp:59-72
     int src = flipbit(pi, r);
@@ -74,6 +47,27 @@ int butterfly_pair(int pi, int r, int Px) {  // conflux_opt.cpp:59-72
     }
     return src;
 }
+#include "init_tables.inc"
+// decodes the fixed input matrix of size n x n (row-major) if the reference has one
+bool fixed_input_matrix(int n, std::vector<double>* out) {
+    for (const InitTable& t : kInitTables) {
+        if (t.n != n) continue;
+        out->clear();
+        out->reserve((size_t)n * n);
+        if (t.kind == 0) {
+            for (const char* p = t.text; *p; ++p) out->push_back((double)(*p - '0'));
+        } else {
+            const char* p = t.text;
+            while (*p) {
+                char* e = nullptr;
+                out->push_back(std::strtod(p, &e));
+                p = (*e == ',') ? e + 1 : e;
+            }
+        }
+        return out->size() == (size_t)n * n;
+    }
+    return false;
+}
 int pick_nb(int v) {  // block size of the diagonal inverses / TRSM sweeps (template instances: 64, 32, 16, 8, 4)
     for (int nb : {64, 32, 16, 8, 4})
         if (v % nb == 0) return nb;
@@ -81,40 +75,7 @@ int pick_nb(int v) {  // block size of the diagonal inverses / TRSM sweeps (temp
 }
 }  // namespace
 
-struct cflx_lu {
-    cflx_comm* comm = nullptr;
-    int M = 0, N = 0, v = 0, Px = 1, Py = 1, Pz = 1, P = 1, Ml = 0, Nl = 0, Nt = 0, Mt = 0, nlayr = 0;
-    int pi = 0, pj = 0, pk = 0, rank = 0, nb = 0;
-    SubComm k_comm, i_comm, jk_comm, ik_comm;
-    // device memory
-    double *A0 = nullptr, *A11 = nullptr, *PT = nullptr, *PT2 = nullptr, *W = nullptr, *LT = nullptr, *A01raw = nullptr,
-           *U = nullptr, *tmp = nullptr, *A00 = nullptr, *A00T = nullptr, *Uinv = nullptr, *LinvT = nullptr,
-           *candH = nullptr, *S = nullptr, *W2 = nullptr, *bcast = nullptr, *Cbuf = nullptr, *xbuf = nullptr;
-    int *gri = nullptr, *gri_tmp = nullptr, *igri = nullptr, *perm = nullptr, *gpivots = nullptr, *tagsH = nullptr,
-        *tagsS = nullptr, *hist = nullptr, *plan_mem = nullptr, *idx_buf = nullptr;
-    MovePlan plan{};
-    PanelWorkspace pws{};
-    int64_t ldp_max = 0;
-    int* h_npiv = nullptr;  // pinned
-    std::vector<int> h_hist;
-    bool have_input = false, factored = false, profiling = false, time_gemm = false;
-    double gemm_ms = 0, gemm_flops = 0;
-    int64_t launches = 0;
-    double phase_ms[PH_COUNT] = {0};
-    std::vector<cudaEvent_t> ev;
-    std::vector<char> ev_used;
-    cudaStream_t side = nullptr;  // high-priority look-ahead stream (null: no overlap)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_npiv = nullptr;
-};
-
-namespace {
-
-template <class T>
-int dmalloc(T** p, size_t n) {
-    CFLX_CUDA(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T) + 4096));  // tail pad: bulk copies may over-read
-    return CFLX_OK;
-}
-
+namespace cflx {
 int make_sub(cflx_comm* c, int color, int key, int size, SubComm* out) {
     out->size = size;
     out->rank = key;
@@ -131,7 +92,15 @@ int make_sub(cflx_comm* c, int color, int key, int size, SubComm* out) {
     }
     return CFLX_OK;
 }
+int grid_barrier(cflx_comm* c) {
+    if (c->world_size > 1)
+        CFLX_NCCL(ncclAllReduce(c->d_scratch, c->d_scratch, 1, ncclDouble, ncclSum, c->world, c->stream));
+    CFLX_CUDA(cudaStreamSynchronize(c->stream));
+    return CFLX_OK;
+}
+}  // namespace cflx
 
+namespace {
 struct PhaseTimer {
     cflx_lu* lu;
     int ph;
@@ -207,23 +176,6 @@ __global__ void stack_kernel(const double* __restrict__ candH, const int* __rest
     }
     if (e < 2 * v) tagsS[e] = tagsH[e];
 }
-__global__ void gather_rows_kernel(const double* __restrict__ A, int64_t lda, const int* __restrict__ src_rows, int nrows,
-                                   int ncols, double* __restrict__ out) {
-    const int i = blockIdx.y;
-    if (i >= nrows) return;
-    const double* s = A + (int64_t)src_rows[i] * lda;
-    double* d = out + (int64_t)i * ncols;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += gridDim.x * blockDim.x) d[c] = s[c];
-}
-__global__ void scatter_rows_kernel(const double* __restrict__ in, int ncols, const int* __restrict__ dst_rows, int nrows,
-                                    double* __restrict__ C, int64_t ldc) {
-    const int i = blockIdx.y;
-    if (i >= nrows) return;
-    const double* s = in + (int64_t)i * ncols;
-    double* d = C + (int64_t)dst_rows[i] * ldc;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += gridDim.x * blockDim.x) d[c] = s[c];
-}
-
 // ---- steps 0 + 1 of iteration k: panel extract (+ layer reduce), local pivot search, tournament.  Runs on stream
 // `s`; with look-ahead that is the high-priority side stream and overlaps the trailing update of iteration k-1.
 // Touches only: PT, W, perm, candH/tagsH/S/W2/tagsS, A00/A00T (outputs consumed by finish_step(k) after the join).
@@ -485,13 +437,6 @@ int finish_step(cflx_lu* lu, int k, int& fnpr) {
     return CFLX_OK;
 }
 
-int grid_barrier(cflx_comm* c) {
-    if (c->world_size > 1)
-        CFLX_NCCL(ncclAllReduce(c->d_scratch, c->d_scratch, 1, ncclDouble, ncclSum, c->world, c->stream));
-    CFLX_CUDA(cudaStreamSynchronize(c->stream));
-    return CFLX_OK;
-}
-
 void free_lu(cflx_lu* lu) {
     if (!lu) return;
     cudaSetDevice(lu->comm->device);
@@ -627,6 +572,22 @@ int cflx_init_matrix_host(int M, int N, int v, int Px, int Py, int Pz, int rank,
     if (rank < 0 || rank >= d[7] || !out) return CFLX_ERR_ARG;
     std::fill(out, out + (size_t)Ml * Nl, 0.0);
     if (rank % Pz != 0) return CFLX_OK;  // layers pk != 0 start at zero (lu_params.hpp:149-155)
+    // lu_params.hpp:157-363: for (padded) M == N in {8, 9, 16, 20, 27, 32} the reference fills a FIXED matrix,
+    // element (gi, gj) of the table at the tile-layout slot of this rank
+    if (d[0] == d[1]) {
+        std::vector<double> tab;
+        if (fixed_input_matrix(d[0], &tab)) {
+            const int n = d[0], pi = rank / (Py * Pz), pj = (rank / Pz) % Py;
+            for (int lr = 0; lr < Ml; ++lr) {
+                const int gi = ((lr / v) * Px + pi) * v + lr % v;
+                for (int lc = 0; lc < Nl; ++lc) {
+                    const int gj = ((lc / v) * Py + pj) * v + lc % v;
+                    out[(size_t)lr * Nl + lc] = tab[(size_t)gi * n + gj];
+                }
+            }
+            return CFLX_OK;
+        }
+    }
     // lu_params.hpp:364-375: mt19937_64(seed + rank), values 5 + U[0,1), tile by tile (lti outer, ltj inner),
     // row-major inside a tile (libs/costa/src/costa/grid2grid/grid_layout.hpp:68-92)
     std::mt19937_64 eng((unsigned long long)(seed + rank));
@@ -857,117 +818,30 @@ int cflx_lu_get_factors(cflx_lu* lu, double* C_host, int* perm_out) {
     CFLX_TRY(cflx_lu_get_permutation(lu, hist.data()));
     if (perm_out) std::memcpy(perm_out, hist.data(), sizeof(int) * lu->M);
     if (lu->pk != 0) return CFLX_OK;  // only layer 0 holds factors
-    const int v = lu->v, Px = lu->Px, Ml = lu->Ml, Nl = lu->Nl;
-    const size_t loc = (size_t)Ml * Nl;
+    const size_t loc = (size_t)lu->Ml * lu->Nl;
     if (!lu->Cbuf) CFLX_TRY(dmalloc(&lu->Cbuf, loc));
-    if (!lu->xbuf) CFLX_TRY(dmalloc(&lu->xbuf, 2 * loc));
-    if (!lu->idx_buf) CFLX_TRY(dmalloc(&lu->idx_buf, 2 * (size_t)Ml));
-    // per source rank: its local row counter; per (src, dst): ordered lists
-    std::vector<int> next_local(Px, 0);
-    std::vector<std::vector<int>> send_rows(Px), recv_rows(Px);  // send_rows[dst] = my local rows; recv_rows[src] = my dest rows
-    for (int q = 0; q < lu->M; ++q) {
-        const int g = hist[q];
-        const int owner = (g / v) % Px;
-        const int lrow = next_local[owner]++;
-        const int k = q / v, i = q % v;
-        const int dst = k % Px, drow = (k / Px) * v + i;
-        if (owner == lu->pi) send_rows[dst].push_back(lrow);
-        if (dst == lu->pi) recv_rows[owner].push_back(drow);
-    }
-    std::vector<int> flat_send, flat_recv;
-    for (int p = 0; p < Px; ++p) flat_send.insert(flat_send.end(), send_rows[p].begin(), send_rows[p].end());
-    for (int p = 0; p < Px; ++p) flat_recv.insert(flat_recv.end(), recv_rows[p].begin(), recv_rows[p].end());
-    if ((int)flat_send.size() != Ml || (int)flat_recv.size() != Ml) {
-        set_last_error("factor redistribution: %zu rows to send, %zu to receive, expected %d", flat_send.size(),
-                       flat_recv.size(), Ml);
-        return CFLX_ERR_STATE;
-    }
-    CFLX_CUDA(cudaMemcpyAsync(lu->idx_buf, flat_send.data(), sizeof(int) * Ml, cudaMemcpyHostToDevice, s));
-    CFLX_CUDA(cudaMemcpyAsync(lu->idx_buf + Ml, flat_recv.data(), sizeof(int) * Ml, cudaMemcpyHostToDevice, s));
-    dim3 grid(std::max(1, std::min(32, Nl / 256)), Ml);
-    double* sendbuf = lu->xbuf;
-    double* recvbuf = lu->xbuf + loc;
-    gather_rows_kernel<<<grid, 256, 0, s>>>(lu->A11, Nl, lu->idx_buf, Ml, Nl, sendbuf);
-    CFLX_CUDA(cudaGetLastError());
-    if (Px > 1) {
-        CFLX_NCCL(ncclGroupStart());
-        size_t so = 0, ro = 0;
-        for (int p = 0; p < Px; ++p) {
-            const size_t ns = send_rows[p].size() * (size_t)Nl, nr = recv_rows[p].size() * (size_t)Nl;
-            if (p == lu->pi) {
-                CFLX_CUDA(cudaMemcpyAsync(recvbuf + ro, sendbuf + so, ns * sizeof(double), cudaMemcpyDeviceToDevice, s));
-            } else {
-                if (ns) CFLX_NCCL(ncclSend(sendbuf + so, ns, ncclDouble, p, lu->i_comm.c, s));
-                if (nr) CFLX_NCCL(ncclRecv(recvbuf + ro, nr, ncclDouble, p, lu->i_comm.c, s));
-            }
-            so += ns;
-            ro += nr;
-        }
-        CFLX_NCCL(ncclGroupEnd());
-    } else {
-        recvbuf = sendbuf;
-    }
-    scatter_rows_kernel<<<grid, 256, 0, s>>>(recvbuf, Nl, lu->idx_buf + Ml, Ml, lu->Cbuf, Nl);
-    CFLX_CUDA(cudaGetLastError());
+    CFLX_TRY(redistribute_pivoted_rows(lu, hist, true, lu->A11, lu->Cbuf));
     if (C_host) CFLX_CUDA(cudaMemcpyAsync(C_host, lu->Cbuf, loc * sizeof(double), cudaMemcpyDeviceToHost, s));
     CFLX_CUDA(cudaStreamSynchronize(s));
     return CFLX_OK;
 }
 
-// ||P A - L U||_F / ||A||_F on the device, with the library's own GEMM.  Single-rank grids only (the factors of a
-// multi-rank grid are validated on the host from cflx_lu_get_factors, see tests/).
-int cflx_lu_residual(cflx_lu* lu, double* rel_out) {
-    if (!lu || !rel_out) return CFLX_ERR_ARG;
+// ||P A - L U||_F (absolute, what the reference's validation build prints, conflux_miniapp.cpp:494-500) and the same
+// relative to ||A||_F, computed on the device grid with the library's own GEMM + NCCL (validate.cu).  COLLECTIVE.
+int cflx_lu_validate(cflx_lu* lu, double* frob_abs_out, double* frob_rel_out) {
+    if (!lu) return CFLX_ERR_ARG;
     if (!lu->factored) {
         set_last_error("residual requested before cflx_lu_factor");
         return CFLX_ERR_STATE;
     }
-    if (lu->P != 1) {
-        set_last_error("cflx_lu_residual supports single-rank grids; use cflx_lu_get_factors + a host check otherwise");
-        return CFLX_ERR_UNSUPPORTED;
-    }
-    cudaStream_t s = lu->comm->stream;
     CFLX_CUDA(cudaSetDevice(lu->comm->device));
-    const int n = lu->N;
-    const size_t nn = (size_t)n * n;
-    double *LT = nullptr, *U = nullptr, *PA = nullptr, *acc = nullptr;
-    int rc = CFLX_OK;
-    auto cleanup = [&]() {
-        cudaFree(LT);
-        cudaFree(U);
-        cudaFree(PA);
-        cudaFree(acc);
-    };
-    if ((rc = dmalloc(&LT, nn)) || (rc = dmalloc(&U, nn)) || (rc = dmalloc(&PA, nn)) || (rc = dmalloc(&acc, 2))) {
-        cleanup();
-        return rc;
-    }
-    // at Px == 1 local row r of A11 is pivoted row r (rows were promoted in pivot order)
-    rc = launch_split_factors(lu->A11, lu->Nl, n, LT, U, s);
-    if (!rc) rc = launch_gather_perm_rows(lu->A0, lu->Nl, lu->hist, n, PA, s);
-    if (!rc && cudaMemsetAsync(acc, 0, 2 * sizeof(double), s) != cudaSuccess) rc = CFLX_ERR_CUDA;
-    if (!rc) {
-        GemmArgs g{};
-        g.M = n; g.N = n; g.K = n;
-        g.AT = LT; g.ldat = n;
-        g.B = U; g.ldb = n;
-        g.C = PA; g.ldc = n;
-        g.D = PA; g.ldd = n;
-        g.alpha = -1.0; g.beta = 1.0;
-        rc = launch_gemm_tn(g, s);
-    }
-    if (!rc) rc = launch_sumsq(PA, (int64_t)nn, acc, s);
-    if (!rc) rc = launch_sumsq(lu->A0, (int64_t)nn, acc + 1, s);
-    double h[2] = {0, 0};
-    if (!rc && cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = CFLX_ERR_CUDA;
-    if (!rc && cudaStreamSynchronize(s) != cudaSuccess) {
-        set_last_error("residual: %s", cudaGetErrorString(cudaGetLastError()));
-        rc = CFLX_ERR_CUDA;
-    }
-    cleanup();
-    if (rc) return rc;
-    *rel_out = std::sqrt(h[0]) / std::sqrt(h[1]);
-    return CFLX_OK;
+    std::vector<int> hist(lu->M);
+    CFLX_TRY(cflx_lu_get_permutation(lu, hist.data()));
+    return lu_residual_grid(lu, hist, frob_abs_out, frob_rel_out);
+}
+int cflx_lu_residual(cflx_lu* lu, double* rel_out) {
+    if (!rel_out) return CFLX_ERR_ARG;
+    return cflx_lu_validate(lu, nullptr, rel_out);
 }
 
 int cflx_host_alloc(size_t bytes, void** out) {

@@ -2,7 +2,10 @@
 // (reference: examples/conflux_miniapp.cpp:39-167).  Ranks are host threads of this process, one GPU each (the image
 // has no MPI); a multi-process launcher would create the cflx_comm from an id shipped by its own transport instead.
 //
-//   conflux_miniapp -N 16384 -b 256 -r 2 [-p 2,2,1] [-t weak]
+//   conflux_miniapp -N 16384 -b 256 -r 2 [-p 2,2,1] [-t weak] [--validate]
+// --validate (or building with -DCONFLUX_WITH_VALIDATION, the reference's compile-time switch) runs the reference's
+// check after the last repetition -- P*A - L*U over the grid, "Total Frobenius norm" (conflux_miniapp.cpp:349-500) --
+// on the GPUs and also prints the norm relative to ||A||_F.
 #include <conflux/lu/conflux_b200.hpp>
 
 #include <cmath>
@@ -15,6 +18,11 @@
 int main(int argc, char** argv) {
     int N = 1000, b = 256, n_rep = 2, grid[3] = {-1, -1, -1};
     std::string type = "other";
+#ifdef CONFLUX_WITH_VALIDATION
+    bool validate = true;
+#else
+    bool validate = false;
+#endif
     for (int i = 1; i < argc; ++i) {
         auto is = [&](const char* s, const char* l) { return !std::strcmp(argv[i], s) || !std::strcmp(argv[i], l); };
         if (is("-N", "--cols") && i + 1 < argc) N = std::atoi(argv[++i]);
@@ -23,6 +31,7 @@ int main(int argc, char** argv) {
         else if (is("-t", "--type") && i + 1 < argc) type = argv[++i];
         else if (is("-p", "--p_grid") && i + 1 < argc) std::sscanf(argv[++i], "%d,%d,%d", &grid[0], &grid[1], &grid[2]);
         else if (is("-l", "--print_limit") && i + 1 < argc) ++i;
+        else if (is("--validate", "--validate")) validate = true;
         else if (is("-h", "--help")) {
             std::puts("conflux miniapp (B200): -N <cols> -b <block> -p Px,Py,Pz -r <reps> -t weak|strong|other");
             return 0;
@@ -54,7 +63,9 @@ int main(int argc, char** argv) {
                     std::cout << "======== INTERNAL PARAMS ========\nRank: 0, M: " << params.M << ", N: " << params.N
                               << ", P:" << params.P << ", v:" << params.v << ", Px:" << params.Px << ", Py: " << params.Py
                               << ", Pz: " << params.Pz << ", Nt: " << params.Nt << ", tA11x: " << params.tA11x
-                              << ", tA11y: " << params.tA11y << "\n======== RESULTS ========" << std::endl;
+                              << ", tA11y: " << params.tA11y << "\n\n======== RESULT FORMAT ========\n"
+                              << "_result_ lu,conflux,<num_rows>,<num_cols>,<num_ranks>,<process_grid>,time,other,<time_in_ms>,<block_size>\n\n"
+                              << "======== RESULTS ========" << std::endl;
                 }
                 std::vector<int> piv(params.M);
                 const int sqrtP = (int)std::sqrt((double)params.P);
@@ -66,6 +77,15 @@ int main(int argc, char** argv) {
                         std::cout << "_result_ lu,conflux," << params.N << "," << N_base << "," << params.P << "," << params.Px
                                   << "x" << params.Py << "x" << params.Pz << ",time," << type << "," << time << "," << params.v
                                   << std::endl;
+                }
+                if (validate) {  // collective; every rank gets the same numbers
+                    double rel = 0;
+                    const double frob = conflux::validate(params, &rel);
+                    if (params.rank == 0) {
+                        std::printf("Total Frobenius norm = %.4f\n", frob);
+                        std::printf("Relative residual ||PA-LU||_F/||A||_F = %.3e\n", rel);
+                        std::fflush(stdout);
+                    }
                 }
             }
             cflx_comm_destroy(comm);

@@ -82,8 +82,12 @@ int cflx_lu_factor(cflx_lu*, double* ms_out);
 int cflx_lu_get_factors(cflx_lu*, double* C_host, int* permutation_out);
 /* device -> host copy of the permutation only (the cheap "result" of a run) */
 int cflx_lu_get_permutation(cflx_lu*, int* permutation_out);
-/* ||P*A - L*U||_F / ||A||_F computed on the device with the library's own GEMM (single-rank grids; allocates 3 n^2
- * doubles temporarily).  The reference prints the absolute norm in its validation build (conflux_miniapp.cpp:494-500). */
+/* COLLECTIVE.  The reference's validation (examples/conflux_miniapp.cpp:349-500: L = unit-lower(C), U = upper(C),
+ * P from the pivots, P*A - L*U with pdgemm on the Px x Py grid, Frobenius norm reduced over the grid) on the GPU grid:
+ * frob_abs_out = ||P*A - L*U||_F (what the reference prints), frob_rel_out = that / ||A||_F.  Either may be NULL.
+ * Uses the library's own GEMM and NCCL; allocates ~4 local matrices temporarily; identical result on every rank. */
+int cflx_lu_validate(cflx_lu*, double* frob_abs_out, double* frob_rel_out);
+/* COLLECTIVE.  = cflx_lu_validate(lu, NULL, rel_out) */
 int cflx_lu_residual(cflx_lu*, double* rel_out);
 /* number of kernels this plan launched since the last call (for bench.py's gpu_launches) */
 int cflx_lu_launch_count(cflx_lu*, int64_t* count_out, int reset);
@@ -106,6 +110,11 @@ int cflx_dbg_panel(int n, int v, const double* panel, int* perm_out, double* A00
                    double* ms_out);
 /* X = B * U^-1 (right, upper, non-unit; B n x v) and Y = L^-1 * R (left, lower, unit; R v x n), A00 = L\U packed */
 int cflx_dbg_trsm(int n, int v, const double* A00, const double* B, double* X_out, const double* R, double* Y_out);
+/* plan_moves + push_phase1..3 + gri bookkeeping on one rank: the npiv pivot rows (local indices >= fnpr, tournament
+ * order) are pushed to rows [fnpr, fnpr+npiv) exactly like push_pivots_up (conflux_opt.hpp:176-218, tests/unit/
+ * test_utils.cpp:8-84).  n_cols even.  gri_out[n_rows] = new row -> old row, a01_out[npiv*n_cols] = extracted rows. */
+int cflx_dbg_push_pivots(int n_rows, int n_cols, double* A_inout, int npiv, const int* pivot_rows, int fnpr, int* gri_out,
+                         double* a01_out);
 /* cycle counters of CTA 0 of the last cflx_dbg_panel launch: {candidate+argmax, exchange, argmax2, row fetch,
  * eliminate, load/write-back, U12 gather+solve, rank update} */
 int cflx_dbg_last_panel_cycles(long long* out8);

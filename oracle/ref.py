@@ -53,3 +53,16 @@ def init_matrix(N, v, Px=1, Py=1, Pz=1):
     A = np.zeros((d["P"], d["Ml"] * d["Nl"]))
     lib().ref_init_matrix(N, v, Px, Py, Pz, _dp(A))
     return [A[r].reshape(d["Ml"], d["Nl"]) for r in range(d["P"])]
+
+
+def lu_bench(N, v, Px=1, Py=1, Pz=1, n_warm=1, n_rep=3, budget_s=300.0, blas_threads=1):
+    """Time-boxed repetition loop inside ONE lu_params object (bench.py --impl reference).  Returns dict(inner_ms=[...],
+    outer_ms=[...]) of the timed repetitions actually done: inner = what LU_rep returns (conflux_opt.hpp:1807)."""
+    inner = np.zeros(max(1, n_rep))
+    outer = np.zeros(max(1, n_rep))
+    done = ctypes.c_int(0)
+    lib().ref_lu_bench.argtypes = [ctypes.c_int] * 7 + [ctypes.c_double, ctypes.POINTER(ctypes.c_double),
+                                                        ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    lib().ref_lu_bench(int(N), int(v), int(Px), int(Py), int(Pz), int(n_warm), int(n_rep), float(budget_s), _dp(inner),
+                       _dp(outer), ctypes.byref(done), int(blas_threads))
+    return dict(inner_ms=inner[:done.value].tolist(), outer_ms=outer[:done.value].tolist())

@@ -8,6 +8,8 @@
 #include <conflux/lu/conflux_opt.hpp>
 #include <conflux/lu/utils.hpp>
 
+#include <atomic>
+#include <chrono>
 #include <cstring>
 #include <vector>
 
@@ -52,7 +54,62 @@ void rank_main(int rank, void* p) {
 }
 }  // namespace
 
+namespace {
+// bench.py --impl reference: ONE lu_params object (= one process, thread pools warm) runs n_warm untimed and then up
+// to n_rep timed factorisations, InitMatrix before each like the miniapp (conflux_miniapp.cpp:138-149), and stops
+// early once budget_s of wall time are spent (at least one timed rep is always done).  Reports what LU_rep itself
+// returns (main loop between two barriers, conflux_opt.hpp:531-532,1805-1807) and the wall time around the call.
+struct BenchArgs {
+    int N, v, Px, Py, Pz, n_warm, n_rep;
+    double budget_s;
+    double* ms_inner;  // [n_rep]
+    double* ms_outer;  // [n_rep]
+    int done;
+    std::atomic<int> stop;
+    std::chrono::steady_clock::time_point t_start;
+};
+void bench_main(int rank, void* p) {
+    auto* a = (BenchArgs*)p;
+    conflux::lu_params<double> params(a->N, a->N, a->v, a->Px, a->Py, a->Pz, MPI_COMM_WORLD);
+    std::vector<double> C((size_t)params.Ml * params.Nl, 0.0);
+    std::vector<int> piv(params.M, -1);
+    for (int i = 0; i < a->n_warm + a->n_rep; ++i) {
+        params.InitMatrix();
+        MPI_Barrier(params.lu_comm);
+        auto t0 = std::chrono::steady_clock::now();
+        std::size_t inner = conflux::LU_rep<double>(params, C.data(), piv.data());
+        MPI_Barrier(params.lu_comm);
+        auto t1 = std::chrono::steady_clock::now();
+        if (params.rank == 0) {
+            if (i >= a->n_warm) {
+                a->ms_inner[i - a->n_warm] = (double)inner;
+                a->ms_outer[i - a->n_warm] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+                a->done = i - a->n_warm + 1;
+            }
+            const double spent = std::chrono::duration<double>(t1 - a->t_start).count();
+            const double last = std::chrono::duration<double>(t1 - t0).count();
+            // stop when the next repetition would not fit the budget any more
+            if (i >= a->n_warm && spent + last > a->budget_s) a->stop.store(1);
+        }
+        MPI_Barrier(params.lu_comm);
+        if (a->stop.load()) break;
+    }
+    MPI_Barrier(params.lu_comm);
+}
+}  // namespace
+
 extern "C" {
+
+int ref_lu_bench(int N, int v, int Px, int Py, int Pz, int n_warm, int n_rep, double budget_s, double* ms_inner,
+                 double* ms_outer, int* done, int blas_threads) {
+    BenchArgs a{N, v, Px, Py, Pz, n_warm < 0 ? 0 : n_warm, n_rep < 1 ? 1 : n_rep, budget_s, ms_inner, ms_outer, 0};
+    a.stop.store(0);
+    a.t_start = std::chrono::steady_clock::now();
+    openblas_set_num_threads(blas_threads > 0 ? blas_threads : 1);
+    stub_mpi_run(Px * Py * Pz, bench_main, &a);
+    *done = a.done;
+    return 0;
+}
 
 // dims_out[6] = {M, N, Ml, Nl, Nt, nlayr} exactly as lu_params::initialize derives them (lu_params.hpp:67-82)
 int ref_lu_dims(int N, int v, int Px, int Py, int Pz, int* dims_out) {

@@ -46,7 +46,7 @@ def run_ranks(P, fn):
     return out
 
 
-def gpu_lu(N, v, Px=1, Py=1, Pz=1, A_locals=None, want_C=True):
+def gpu_lu(N, v, Px=1, Py=1, Pz=1, A_locals=None, want_C=True, want_resid=False):
     """Runs the CUDA path on a Px x Py x Pz grid.  Returns dict(A=[...], C=[...], perm, ms, dims)."""
     P = Px * Py * Pz
 
@@ -58,10 +58,13 @@ def gpu_lu(N, v, Px=1, Py=1, Pz=1, A_locals=None, want_C=True):
         perm = np.full(gv.M, -1, dtype=np.int32)
         ms = cb.LU_rep(gv, C, perm)
         res = dict(A=gv.data.copy(), C=C, perm=perm, ms=ms, rank=gv.rank)
+        if want_resid:
+            res["resid_abs"], res["resid"] = cb.validate(gv)              # collective, on the GPU grid
         gv.free_comms()
         return res
 
     rs = run_ranks(P, body)
     d = layout.dims(N, v, Px, Py, Pz)
     return dict(A=[r["A"] for r in rs], C=[r["C"] for r in rs], perm=rs[0]["perm"], perms=[r["perm"] for r in rs],
-                ms=max(r["ms"] for r in rs), dims=d)
+                ms=max(r["ms"] for r in rs), dims=d, resid=[r.get("resid") for r in rs],
+                resid_abs=[r.get("resid_abs") for r in rs])

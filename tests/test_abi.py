@@ -46,6 +46,25 @@ def test_init_matrix_host_is_the_reference_generator():
             assert np.array_equal(cb.init_matrix_host(N, N, v, *g, rank), ref[rank])
 
 
+def test_fixed_input_matrices_are_the_references(golden_dir):
+    """lu_params.hpp:157-363: for (padded) M == N in {8, 9, 16, 20, 27, 32} InitMatrix fills a FIXED matrix.  The golden
+    fixtures hold what the reference itself produced on several grids (tests/golden/make_golden.py)."""
+    G = np.load(os.path.join(golden_dir, "lu_cases.npz"))
+    seen = set()
+    for i, (N, v, Px, Py, Pz) in enumerate(G["cases"]):
+        if int(N) not in (16, 27, 32):
+            continue
+        for rank in range(int(Px * Py * Pz)):
+            mine = cb.init_matrix_host(int(N), int(N), int(v), int(Px), int(Py), int(Pz), rank)
+            assert np.array_equal(mine.reshape(-1), G[f"c{i}_A"][rank].reshape(-1)), (N, v, Px, Py, Pz, rank)
+        seen.add(int(N))
+    assert seen == {16, 27, 32}
+    # padding reaches a fixed size too: N = 30, v = 4, Px = 2 is padded to 32 and takes the 32 x 32 table
+    a = cb.init_matrix_host(30, 30, 4, 2, 2, 1, 0)
+    b = cb.init_matrix_host(32, 32, 4, 2, 2, 1, 0)
+    assert np.array_equal(a, b) and float(a.max()) <= 9.0
+
+
 def test_device_entry_points_refuse_without_gpu():
     n = ctypes.c_int(-1)
     assert _lib.lib().cflx_device_count(ctypes.byref(n)) == 0

@@ -68,6 +68,26 @@ def test_trsm_matches_numpy(n, v):
     assert np.abs(L @ Y - R).max() <= 1e-10 * np.abs(R).max() * v
 
 
+def test_push_pivots_reference_unit_vector_and_seeded_cases(golden_dir):
+    """plan_moves + push_phase1..3 in isolation on the reference's own unit-test input (tests/unit/test_utils.cpp:8-84:
+    pivots {2,1,5}, expected row order [2,1,5,3,4,0,6,7]) and on the seeded cases the reference itself produced
+    (tests/golden/helpers.npz; the kernels move 128-bit pairs, so the odd-width cases are run with one padding column)."""
+    import os
+    H = np.load(os.path.join(golden_dir, "helpers.npz"))
+    A, gri, a01 = cb.dbg.push_pivots(H["push0_in"], H["push0_piv"][1:], 0)
+    assert np.array_equal(A, H["push0_in"][[2, 1, 5, 3, 4, 0, 6, 7]]) and np.array_equal(A, H["push0_out"])
+    assert gri.tolist() == [2, 1, 5, 3, 4, 0, 6, 7]
+    assert np.array_equal(a01, H["push0_in"][[2, 1, 5]])
+    for i in range(int(H["push_n"])):
+        m, cp, fnpr, out = H[f"push{i}_in"], H[f"push{i}_piv"], int(H[f"push{i}_fnpr"]), H[f"push{i}_out"]
+        pad = m.shape[1] & 1
+        mp = np.concatenate([m, np.arange(m.shape[0], dtype=np.float64)[:, None]], axis=1) if pad else m
+        A, gri, _ = cb.dbg.push_pivots(mp, cp[1:1 + cp[0]], fnpr)
+        assert np.array_equal(A[:, :m.shape[1]], out), i
+        if pad:
+            assert np.array_equal(A[:, -1], gri.astype(np.float64)), i      # the padding column travelled with its row
+
+
 def test_fp64_pipe_probe_runs():
     dmma, dfma = cb.dbg.fp64_peak(0), cb.dbg.fp64_peak(1)
     print(f"FP64 peaks: DMMA {dmma:.1f} TFLOP/s, DFMA {dfma:.1f} TFLOP/s")
