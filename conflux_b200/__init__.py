@@ -15,7 +15,7 @@ import numpy as np
 
 from ._lib import ConfluxError, LIB_PATH, SYMBOLS, check, lib
 
-__all__ = ["pinned_empty", "pinned_free", "Comm", "lu_params", "LU_rep", "residual", "validate", "auto_grid", "lu_dims", "init_matrix_host", "ConfluxError", "dbg"]
+__all__ = ["pinned_empty", "pinned_free", "Comm", "lu_params", "LU_rep", "residual", "validate", "timeline", "auto_grid", "lu_dims", "init_matrix_host", "ConfluxError", "dbg"]
 
 
 def auto_grid(M, N, P):
@@ -171,6 +171,16 @@ def LU_rep(gv, C=None, permutation=None, upload=True):
     return ms.value
 
 
+def timeline(gv):
+    """Per-region device time of the last LU_rep run under cflx_lu_set_profiling(gv._h, 1 or 2): dict(main={region: (ms,
+    count)}, side={...}); region names are the reference's semiprof regions."""
+    import json
+    n = lib().cflx_lu_timeline(gv._h, None, 0)
+    buf = ctypes.create_string_buffer(max(n, 2))
+    check(lib().cflx_lu_timeline(gv._h, buf, n), "lu_timeline")
+    return json.loads(buf.value.decode())
+
+
 def validate(gv):
     """The reference's validation (examples/conflux_miniapp.cpp:349-500) of the last LU_rep on the GPU grid.
     COLLECTIVE over gv.lu_comm.  Returns (||PA - LU||_F, ||PA - LU||_F / ||A||_F), identical on every rank."""
@@ -231,6 +241,25 @@ class dbg:
                                   X.ctypes.data if X is not None else None, R.ctypes.data if R is not None else None,
                                   Y.ctypes.data if Y is not None else None), "dbg_trsm")
         return X, Y
+
+    @staticmethod
+    def ozaki_gemm(AT, B, C=None, reps=1, want_planes=False):
+        """D = C - AT^T @ B on the int8 tcgen05 path.  Returns dict(D, ms, split_ms[, pa, pb, ea, eb])."""
+        AT = np.ascontiguousarray(AT, dtype=np.float64)
+        B = np.ascontiguousarray(B, dtype=np.float64)
+        K, M = AT.shape
+        N = B.shape[1]
+        D = np.empty((M, N))
+        Cp = np.ascontiguousarray(C, dtype=np.float64) if C is not None else None
+        pa = np.zeros((8, M, K), dtype=np.int8) if want_planes else None
+        pb = np.zeros((8, N, K), dtype=np.int8) if want_planes else None
+        ea = np.zeros(M, dtype=np.int32) if want_planes else None
+        eb = np.zeros(N, dtype=np.int32) if want_planes else None
+        ms, sms = ctypes.c_double(), ctypes.c_double()
+        ptr = lambda a: a.ctypes.data if a is not None else None
+        check(lib().cflx_dbg_ozaki_gemm(M, N, K, AT.ctypes.data, B.ctypes.data, ptr(Cp), D.ctypes.data, ptr(pa), ptr(pb), ptr(ea),
+                                        ptr(eb), int(reps), ctypes.byref(ms), ctypes.byref(sms)), "dbg_ozaki_gemm")
+        return dict(D=D, ms=ms.value, split_ms=sms.value, pa=pa, pb=pb, ea=ea, eb=eb)
 
     @staticmethod
     def push_pivots(A, pivot_rows, fnpr):

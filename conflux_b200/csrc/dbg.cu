@@ -301,4 +301,77 @@ int cflx_dbg_push_pivots(int n_rows, int n_cols, double* A_inout, int npiv, cons
     return CFLX_OK;
 }
 
+// D = C - AT^T * B on the int8 tcgen05 path (ozaki.cu): AT [K x M], B [K x N], C/D [M x N] row-major dense host arrays,
+// K a multiple of 128, N even.  Optional outputs for tests: the digit planes [8][M][K] / [8][N][K] (int8) and the
+// exponents [M] / [N], exactly as the kernels produced them.  ms_out = mean device time of the GEMM kernel alone.
+int cflx_dbg_ozaki_gemm(int M, int N, int K, const double* AT, const double* B, const double* C, double* D,
+                        signed char* planesA_out, signed char* planesB_out, int* ea_out, int* eb_out, int reps,
+                        double* ms_out, double* split_ms_out) {
+    CFLX_TRY(check_device());
+    if (M <= 0 || N <= 0 || K <= 0 || (N & 1)) return CFLX_ERR_ARG;
+    const int64_t ldat = round_up(M, 2), ldb = N, ldc = N;
+    DevBuf dA, dB, dC, dC0;
+    CFLX_TRY(dA.alloc(sizeof(double) * K * ldat));
+    CFLX_TRY(dB.alloc(sizeof(double) * K * ldb));
+    CFLX_TRY(dC.alloc(sizeof(double) * M * ldc));
+    CFLX_TRY(dC0.alloc(sizeof(double) * M * ldc));
+    CFLX_CUDA(cudaMemset(dA.p, 0, sizeof(double) * K * ldat));
+    CFLX_CUDA(cudaMemcpy2D(dA.p, ldat * 8, AT, (size_t)M * 8, (size_t)M * 8, K, cudaMemcpyHostToDevice));
+    CFLX_CUDA(cudaMemcpy(dB.p, B, sizeof(double) * K * ldb, cudaMemcpyHostToDevice));
+    if (C) CFLX_CUDA(cudaMemcpy(dC0.p, C, sizeof(double) * M * ldc, cudaMemcpyHostToDevice));
+    else CFLX_CUDA(cudaMemset(dC0.p, 0, sizeof(double) * M * ldc));
+    OzakiWorkspace ws;
+    int rc = ozaki_workspace_create(&ws, M, N, K);
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventCreate(&e2);
+    if (reps < 1) reps = 1;
+    float ms = 0, ms_split = 0;
+    for (int r = 0; r < reps + 1 && rc == CFLX_OK; ++r) {
+        cudaMemcpyAsync(dC.p, dC0.p, sizeof(double) * M * ldc, cudaMemcpyDeviceToDevice, 0);
+        cudaEventRecord(e0);
+        rc = ozaki_split_a(&ws, dA.as<double>(), ldat, M, 0);
+        if (!rc) rc = ozaki_split_b(&ws, dB.as<double>(), ldb, 0, N, 0);
+        cudaEventRecord(e1);
+        if (!rc) rc = launch_ozaki_gemm(&ws, M, N, 0, dC.as<double>(), ldc, 0, 0);
+        cudaEventRecord(e2);
+        if (cudaEventSynchronize(e2) != cudaSuccess) {
+            set_last_error("ozaki kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = CFLX_ERR_CUDA;
+        }
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, e0, e1);
+        cudaEventElapsedTime(&b, e1, e2);
+        if (r > 0) {
+            ms_split += a;
+            ms += b;
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    if (rc == CFLX_OK) {
+        if (D) cudaMemcpy(D, dC.p, sizeof(double) * M * ldc, cudaMemcpyDeviceToHost);
+        for (int s = 0; s < 8; ++s) {
+            if (planesA_out) cudaMemcpy(planesA_out + (size_t)s * M * K, ws.planesA + (size_t)s * ws.cap_a * K, (size_t)M * K, cudaMemcpyDeviceToHost);
+            if (planesB_out) cudaMemcpy(planesB_out + (size_t)s * N * K, ws.planesB + (size_t)s * ws.cap_b * K, (size_t)N * K, cudaMemcpyDeviceToHost);
+        }
+        if (ea_out) cudaMemcpy(ea_out, ws.ea, sizeof(int) * M, cudaMemcpyDeviceToHost);
+        if (eb_out) cudaMemcpy(eb_out, ws.eb, sizeof(int) * N, cudaMemcpyDeviceToHost);
+        if (ws.dbg) {
+            long long h[16];
+            cudaMemcpy(h, ws.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[ozaki cycles, CTA 0] producer: wait emptyB %lld emptyA %lld total %lld | mma: wait fullA %lld fullB %lld tempty %lld "
+                            "total %lld | epilogue: wait tfull %lld drain %lld rmw %lld total %lld\n",
+                    h[0], h[1], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11]);
+        }
+        if (cudaDeviceSynchronize() != cudaSuccess) rc = CFLX_ERR_CUDA;
+    }
+    ozaki_workspace_destroy(&ws);
+    if (ms_out) *ms_out = ms / reps;
+    if (split_ms_out) *split_ms_out = ms_split / reps;
+    return rc;
+}
+
 }  // extern "C"

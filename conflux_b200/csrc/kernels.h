@@ -23,6 +23,24 @@ struct GemmArgs {
 int gemm_tn_setup();
 int launch_gemm_tn(const GemmArgs& g, cudaStream_t stream);
 
+// ---------------------------------------------------------------- ozaki.cu
+// FP64 trailing update on the int8 tcgen05 path (error-free digit planes): C -= L * U with L^T, U K-major in HBM.
+struct OzakiWorkspace {
+    struct Maps;              // the two CUtensorMap objects (kept out of this header)
+    int8_t* planesA = nullptr;  // [8][cap_a][K]
+    int8_t* planesB = nullptr;  // [8][cap_b][K]
+    int* ea = nullptr;          // [cap_a]
+    int* eb = nullptr;          // [cap_b]
+    long long* dbg = nullptr;   // [16] cycle counters of CTA 0 (CFLX_OZAKI_DBG=1)
+    Maps* maps = nullptr;
+    int K = 0, cap_a = 0, cap_b = 0, sms = 0;
+};
+int ozaki_workspace_create(OzakiWorkspace* ws, int max_rows, int max_cols, int K);
+void ozaki_workspace_destroy(OzakiWorkspace* ws);
+int ozaki_split_a(OzakiWorkspace* ws, const double* LT, int64_t ld, int n, cudaStream_t s);
+int ozaki_split_b(OzakiWorkspace* ws, const double* U, int64_t ld, int col0, int n, cudaStream_t s);
+int launch_ozaki_gemm(OzakiWorkspace* ws, int M, int N, int col0, double* C, int64_t ldc, int max_ctas, cudaStream_t s);
+
 // ---------------------------------------------------------------- panel.cu
 // Partial-pivot LU of the n x v panel stored TRANSPOSED in W (W[c][r], ld = ldw), in place, rows never move:
 // afterwards W[:, r] holds row r of L\U (multipliers left of its pivot column, U from it on, for pivot rows;

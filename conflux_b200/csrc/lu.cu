@@ -18,7 +18,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <random>
+#include <string>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "lu_state.h"
 
@@ -101,27 +104,47 @@ int grid_barrier(cflx_comm* c) {
 }  // namespace cflx
 
 namespace {
+// One profiling region: always an NVTX range named like the reference's semiprof region; with profiling mode 1 a
+// serialising CUDA-event timer (accurate per-phase device time, no overlap), with mode 2 an event pair on the launching
+// stream that is resolved after the factorisation (no synchronisation: the timeline of the real, overlapped run).
 struct PhaseTimer {
     cflx_lu* lu;
-    int ph;
+    int rg;
+    cudaStream_t st;
     cudaEvent_t a = nullptr, b = nullptr;
-    PhaseTimer(cflx_lu* l, int p) : lu(l), ph(p) {
-        if (lu->profiling) {
+    int ev = -1;
+    PhaseTimer(cflx_lu* l, int region, cudaStream_t stream) : lu(l), rg(region), st(stream) {
+        nvtxRangePushA(region_name(rg));
+        if (lu->prof_mode == 1) {
             cudaEventCreate(&a);
             cudaEventCreate(&b);
-            cudaEventRecord(a, lu->comm->stream);
+            cudaEventRecord(a, st);
+        } else if (lu->prof_mode == 2) {
+            ev = (int)lu->tl_recs.size() * 2;
+            while ((int)lu->tl_pool.size() < ev + 2) {
+                cudaEvent_t e;
+                cudaEventCreate(&e);
+                lu->tl_pool.push_back(e);
+            }
+            lu->tl_recs.push_back({rg, st == lu->comm->stream ? 0 : 1, ev});
+            cudaEventRecord(lu->tl_pool[ev], st);
         }
     }
     ~PhaseTimer() {
-        if (lu->profiling) {
-            cudaEventRecord(b, lu->comm->stream);
+        if (lu->prof_mode == 1) {
+            cudaEventRecord(b, st);
             cudaEventSynchronize(b);
             float ms = 0;
             cudaEventElapsedTime(&ms, a, b);
-            lu->phase_ms[ph] += ms;
+            lu->phase_ms[region_phase(rg)] += ms;
+            lu->region_ms[st == lu->comm->stream ? 0 : 1][rg] += ms;
+            lu->region_cnt[st == lu->comm->stream ? 0 : 1][rg]++;
             cudaEventDestroy(a);
             cudaEventDestroy(b);
+        } else if (lu->prof_mode == 2) {
+            cudaEventRecord(lu->tl_pool[ev + 1], st);
         }
+        nvtxRangePop();
     }
 };
 
@@ -194,18 +217,23 @@ int panel_phase(cflx_lu* lu, int k, int fnpr, cudaStream_t s) {
     while ((1 << nR) < Px) ++nR;
     // ---- step 0: panel extract (+ reduce over layers onto pk = 0)            conflux_opt.hpp:618-648
     {
-        PhaseTimer t(lu, PH_PANEL);
+        PhaseTimer t(lu, RG_step0_copy, s);
         CFLX_TRY(launch_extract_panel_T(lu->A11, Nl, fnpr, loff, n_old, v, lu->PT, ldk, s));
         lu->launches++;
-        if (Pz > 1 && n_old > 0)
-            CFLX_NCCL(ncclReduce(lu->PT, lu->PT, (size_t)v * ldk, ncclDouble, ncclSum, 0, lu->k_comm.c, s));
+    }
+    if (Pz > 1 && n_old > 0) {
+        PhaseTimer t(lu, RG_step0_reduce, s);
+        CFLX_NCCL(ncclReduce(lu->PT, lu->PT, (size_t)v * ldk, ncclDouble, ncclSum, 0, lu->k_comm.c, s));
     }
     if (pk != 0) return CFLX_OK;
     // ---- step 1: local pivot search + tournament on column pj == k % Py, layer 0   conflux_opt.hpp:693-816
     int my_half = 0;
     {
-        PhaseTimer t(lu, PH_PANEL);
+        PhaseTimer t(lu, RG_step1_A10copy, s);
         CFLX_CUDA(cudaMemcpyAsync(lu->W, lu->PT, (size_t)v * ldk * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    }
+    {
+        PhaseTimer t(lu, RG_step1_lup, s);
         int nb_used = 0;
         if (nR == 0) {  // the local search already is the tournament: A00 comes from it
             CFLX_TRY(launch_panel_getrf_a00(lu->W, ldk, n_old, v, lu->perm, A00, &nb_used, &lu->pws, s));
@@ -215,6 +243,9 @@ int panel_phase(cflx_lu* lu, int k, int fnpr, cudaStream_t s) {
             CFLX_TRY(launch_panel_getrf(lu->W, ldk, n_old, v, lu->perm, &lu->pws, s));
             lu->launches++;
         }
+    }
+    {
+        PhaseTimer t(lu, RG_step1_rowpermute, s);
         int first_partner = flipbit(pi, 0);
         if (first_partner > Px - 1) first_partner = Px - 1;
         my_half = first_partner < pi ? 1 : 0;  // "higher rank puts his candidates below" (conflux_opt.hpp:717-750)
@@ -222,7 +253,7 @@ int panel_phase(cflx_lu* lu, int k, int fnpr, cudaStream_t s) {
                                        lu->candH + (size_t)my_half * v * v, v, lu->tagsH + my_half * v, 0, s));
         lu->launches++;
     }
-    PhaseTimer t(lu, PH_TOURN);
+    PhaseTimer t(lu, RG_step1_pivoting, s);
     for (int r = 0; r < nR; ++r) {
         CFLX_TRY(tournament_exchange(lu, r, my_half, s));
         const int64_t tot = (int64_t)2 * v * v;
@@ -247,10 +278,24 @@ int panel_phase(cflx_lu* lu, int k, int fnpr, cudaStream_t s) {
     return CFLX_OK;
 }
 
+// digit planes of the operands of this step's trailing update (int8 tcgen05 path): L^T slab of this layer, U slab columns
+int ozaki_planes_a(cflx_lu* lu, int n_act, int64_t ld2, cudaStream_t s) {
+    if (!lu->use_ozaki || n_act <= 0) return CFLX_OK;
+    PhaseTimer t(lu, RG_step6_dgemm, s);
+    lu->launches++;
+    return ozaki_split_a(&lu->oz, lu->LT + (int64_t)lu->pk * lu->nlayr * ld2, ld2, n_act, s);
+}
+int ozaki_planes_b(cflx_lu* lu, int col0, int n, int64_t ldu, cudaStream_t s) {
+    if (!lu->use_ozaki || n <= 0) return CFLX_OK;
+    PhaseTimer t(lu, RG_step6_dgemm, s);
+    lu->launches++;
+    return ozaki_split_b(&lu->oz, lu->U + (int64_t)lu->pk * lu->nlayr * ldu, ldu, col0, n, s);
+}
+
 int trailing_gemm(cflx_lu* lu, int k, int part, int fnpr, int n_act, int col_lo, int ncols, int64_t ld2, int64_t ldu,
-                  int u_col_off, cudaStream_t s) {
+                  int u_col_off, cudaStream_t s, int max_ctas = 0) {
     if (n_act <= 0 || ncols <= 0) return CFLX_OK;
-    PhaseTimer t(lu, PH_GEMM);
+    PhaseTimer t(lu, RG_step6_dgemm, s);
     GemmArgs g{};
     g.M = n_act;
     g.N = ncols;
@@ -267,7 +312,8 @@ int trailing_gemm(cflx_lu* lu, int k, int part, int fnpr, int n_act, int col_lo,
     g.beta = 1.0;
     const int e = 4 * k + 2 * part;
     if (lu->time_gemm) CFLX_CUDA(cudaEventRecord(lu->ev[e], s));
-    CFLX_TRY(launch_gemm_tn(g, s));
+    if (lu->use_ozaki) CFLX_TRY(launch_ozaki_gemm(&lu->oz, g.M, g.N, u_col_off, g.D, g.ldd, max_ctas, s));
+    else CFLX_TRY(launch_gemm_tn(g, s));
     if (lu->time_gemm) CFLX_CUDA(cudaEventRecord(lu->ev[e + 1], s));
     lu->ev_used[e / 2] = lu->time_gemm;
     lu->gemm_flops += 2.0 * g.M * (double)g.N * g.K;
@@ -294,7 +340,7 @@ int finish_step(cflx_lu* lu, int k, int& fnpr) {
     double* A00T = lu->A00T + (size_t)(k & 1) * v * v;
     // ---- A00 + pivot ids to everybody (one broadcast)                     conflux_opt.hpp:818-850,872
     {
-        PhaseTimer t(lu, PH_TOURN);
+        PhaseTimer t(lu, RG_step1_A00Buff_bcast, s);
         if (lu->P > 1) {
             const int root = (pik * Py + pjk) * Pz;  // rank of (k % Px, k % Py, 0)
             if (lu->rank == root) {
@@ -315,7 +361,7 @@ int finish_step(cflx_lu* lu, int k, int& fnpr) {
     // on it -- row moves, pivot-row reduce, the U solve, its broadcast, the factor stores -- is enqueued first, and
     // the host only then waits for the 4-byte read-back, so the GPU stays busy while the rest is enqueued.
     {
-        PhaseTimer t(lu, PH_MOVES);
+        PhaseTimer t(lu, RG_step2_pushingpivots, s);
         CFLX_TRY(launch_plan_moves(lu->gpivots, v, Px, pi, fnpr_old, Ml, lu->igri, lu->plan, s));
         lu->launches++;
         if (Px > 1) {
@@ -337,12 +383,12 @@ int finish_step(cflx_lu* lu, int k, int& fnpr) {
     const bool fused_l = (nR == 0);
     // ---- steps 2b/3: pivot rows summed over layers and gathered on row pi == k % Px   conflux_opt.hpp:1164-1260
     if (ncols > 0 && Px * Pz > 1) {
-        PhaseTimer t(lu, PH_REDUCE);
+        PhaseTimer t(lu, RG_step2_reduce, s);
         CFLX_NCCL(ncclReduce(lu->A01raw, lu->A01raw, (size_t)v * ldu, ncclDouble, ncclSum, pik * Pz, lu->ik_comm.c, s));
     }
     // ---- step 5 first: U = L00^-1 * (pivot rows)                            conflux_opt.hpp:1522-1593
     if (layer0 && ((on_col && !fused_l) || on_row)) {
-        PhaseTimer t(lu, PH_TRSM);
+        PhaseTimer t(lu, RG_step5_dtrsm, s);
         CFLX_TRY(launch_diag_inverses(A00, v, lu->nb, lu->Uinv, lu->LinvT, s));
         lu->launches++;
     }
@@ -352,17 +398,17 @@ int finish_step(cflx_lu* lu, int k, int& fnpr) {
     const bool split_u = (lu->P == 1) && (k + 1 < lu->Nt) && ncols > v;
     const int ncols_a = split_u ? v : ncols;
     if (on_row && layer0 && ncols > 0) {
-        PhaseTimer t(lu, PH_TRSM);
+        PhaseTimer t(lu, RG_step5_dtrsm, s);
         CFLX_TRY(trsm_left_lower_unit(A00T, lu->LinvT, v, lu->nb, lu->A01raw, lu->U, ldu, ncols_a, s));
         lu->launches += 2 * (v / lu->nb) - 1;
     }
     if (Px * Pz > 1 && ncols > 0) {  // U panel to every (pi', pk') of my grid column   conflux_opt.hpp:1567-1593
-        PhaseTimer t(lu, PH_REDUCE);
+        PhaseTimer t(lu, RG_step5_comm, s);
         CFLX_NCCL(ncclBroadcast(lu->U, lu->U, (size_t)v * ldu, ncclDouble, pik * Pz, lu->ik_comm.c, s));
     }
     auto store_factors = [&]() -> int {  // my promoted rows receive their U part and diagonal block   :1721-1754
         if (!layer0) return CFLX_OK;
-        PhaseTimer t(lu, PH_STORE);
+        PhaseTimer t(lu, RG_storingresults, s);
         if (ncols > 0) {
             CFLX_TRY(launch_store_u_rows(lu->A11, Nl, fnpr_old, lu->plan, lu->U, ldu, c0, ncols, v, s));
             lu->launches++;
@@ -390,32 +436,34 @@ int finish_step(cflx_lu* lu, int k, int& fnpr) {
     // ---- step 4: L = A10 * U00^-1 on the panel column                       conflux_opt.hpp:1329-1434
     if (on_col && layer0 && n_act > 0) {
         {
-            PhaseTimer t(lu, PH_MOVES);
+            PhaseTimer t(lu, RG_step4_reshuffling, s);
             CFLX_TRY(launch_compact_panel(fused_l ? lu->W : lu->PT, ldk, fused_l ? lu->LT : lu->PT2, ld2, lu->plan.rowsrc,
                                           fnpr_old, lu->plan.npiv, Ml, v, s));
             lu->launches++;
         }
         if (!fused_l) {
-            PhaseTimer t(lu, PH_TRSM);
+            PhaseTimer t(lu, RG_step4_dtrsm, s);
             CFLX_TRY(trsm_right_upper_T(A00, lu->Uinv, v, lu->nb, lu->PT2, lu->LT, ld2, n_act, s));
             lu->launches += 2 * (v / lu->nb) - 1;
         }
-        PhaseTimer t(lu, PH_STORE);
+        PhaseTimer t(lu, RG_storingresults, s);
         CFLX_TRY(launch_store_panel_T(lu->A11, Nl, fnpr, loff, n_act, v, lu->LT, ld2, s));  // L in place
         lu->launches++;
     }
     if (Py * Pz > 1 && n_act > 0) {  // L panel to every (pj', pk') of my grid row    conflux_opt.hpp:1404-1434
-        PhaseTimer t(lu, PH_REDUCE);
+        PhaseTimer t(lu, RG_step4_comm, s);
         CFLX_NCCL(ncclBroadcast(lu->LT, lu->LT, (size_t)v * ld2, ncclDouble, pjk * Pz, lu->jk_comm.c, s));
     }
     // ---- step 6: trailing update on every rank and layer                    conflux_opt.hpp:1628-1632
     // Look-ahead: the rank that owns panel k+1 updates those v columns first (they are its first live block), forks
     // the pivot search of iteration k+1 onto the side stream, and only then updates the remaining columns.
     const bool next_col = (k + 1 < lu->Nt) && (pj == (k + 1) % Py);
+    CFLX_TRY(ozaki_planes_a(lu, n_act, ld2, s));
+    if (n_act > 0) CFLX_TRY(ozaki_planes_b(lu, 0, split_u ? std::min(v, ncols) : ncols, ldu, s));
     if (next_col) {
         const int w = std::min(v, ncols);
         CFLX_TRY(trailing_gemm(lu, k, 0, fnpr, n_act, c0, w, ld2, ldu, 0, s));
-        cudaStream_t side = lu->profiling ? nullptr : lu->side;  // phase profiling serialises everything
+        cudaStream_t side = (lu->prof_mode == 1) ? nullptr : lu->side;  // phase profiling serialises everything
         cudaStream_t sp = side ? side : s;
         if (side) {
             CFLX_CUDA(cudaEventRecord(lu->ev_fork, s));
@@ -424,12 +472,15 @@ int finish_step(cflx_lu* lu, int k, int& fnpr) {
         CFLX_TRY(panel_phase(lu, k + 1, fnpr, sp));
         if (side) CFLX_CUDA(cudaEventRecord(lu->ev_join, sp));
         if (split_u) {
-            PhaseTimer t(lu, PH_TRSM);
+            PhaseTimer t(lu, RG_step5_dtrsm, s);
             CFLX_TRY(trsm_left_lower_unit(A00T, lu->LinvT, v, lu->nb, lu->A01raw + v, lu->U + v, ldu, ncols - v, s));
             lu->launches += 2 * (v / lu->nb) - 1;
         }
         if (split_u) CFLX_TRY(store_factors());
-        CFLX_TRY(trailing_gemm(lu, k, 1, fnpr, n_act, c0 + w, ncols - w, ld2, ldu, w, s));
+        if (split_u && n_act > 0) CFLX_TRY(ozaki_planes_b(lu, w, ncols - w, ldu, s));
+        // the persistent tcgen05 kernel leaves the SMs of the concurrent pivot search alone
+        const int leave = (side && lu->use_ozaki) ? lu->pws.cta_cap : 0;
+        CFLX_TRY(trailing_gemm(lu, k, 1, fnpr, n_act, c0 + w, ncols - w, ld2, ldu, w, s, leave > 0 ? lu->oz.sms - leave : 0));
         if (side) CFLX_CUDA(cudaStreamWaitEvent(s, lu->ev_join, 0));
     } else {
         CFLX_TRY(trailing_gemm(lu, k, 0, fnpr, n_act, c0, ncols, ld2, ldu, 0, s));
@@ -448,7 +499,9 @@ void free_lu(cflx_lu* lu) {
     for (int* p : ints) cudaFree(p);
     if (lu->h_npiv) cudaFreeHost(lu->h_npiv);
     if (lu->pws.slot_hdr) panel_workspace_destroy(&lu->pws);
+    if (lu->use_ozaki) ozaki_workspace_destroy(&lu->oz);
     for (auto& e : lu->ev) cudaEventDestroy(e);
+    for (auto& e : lu->tl_pool) cudaEventDestroy(e);
     if (lu->side) cudaStreamDestroy(lu->side);
     if (lu->ev_fork) cudaEventDestroy(lu->ev_fork);
     if (lu->ev_join) cudaEventDestroy(lu->ev_join);
@@ -669,6 +722,14 @@ int cflx_lu_create(cflx_comm* c, int M, int N, int v, int Px, int Py, int Pz, cf
     if (cudaEventCreateWithFlags(&lu->ev_npiv, cudaEventDisableTiming) != cudaSuccess) return fail(CFLX_ERR_CUDA);
     if ((rc = panel_workspace_create(&lu->pws))) return fail(rc);
     if ((rc = gemm_tn_setup())) return fail(rc);
+    {
+        // CFLX_GEMM=ozaki: trailing update on the int8 tcgen05 path (needs whole 128-element k chunks per layer)
+        const char* e = getenv("CFLX_GEMM");
+        if (e && !strcmp(e, "ozaki") && lu->nlayr % 128 == 0 && lu->nlayr <= 512) {
+            if ((rc = ozaki_workspace_create(&lu->oz, lu->Ml, lu->Nl, lu->nlayr))) return fail(rc);
+            lu->use_ozaki = true;
+        }
+    }
     lu->h_hist.assign(lu->M, -1);
     {
         // look-ahead: pivot search of iteration k+1 (extract, layer reduce, local search, tournament exchanges) on a
@@ -731,9 +792,15 @@ int cflx_lu_factor(cflx_lu* lu, double* ms_out) {
     CFLX_CUDA(cudaSetDevice(c->device));
     const size_t loc = (size_t)lu->Ml * lu->Nl;
     // "init" region of the reference (conflux_opt.hpp:347-515): A11Buff = copy of gv.data, gri, counters
-    CFLX_CUDA(cudaMemcpyAsync(lu->A11, lu->A0, loc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    {
+        PhaseTimer t(lu, RG_init, s);
+        CFLX_CUDA(cudaMemcpyAsync(lu->A11, lu->A0, loc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    }
     CFLX_TRY(launch_iota_gri(lu->gri, lu->igri, lu->Ml, lu->v, lu->Px, lu->pi, s));
     for (double& x : lu->phase_ms) x = 0;
+    for (int sd = 0; sd < 2; ++sd)
+        for (int r = 0; r < RG_COUNT; ++r) lu->region_ms[sd][r] = 0, lu->region_cnt[sd][r] = 0;
+    lu->tl_recs.clear();
     CFLX_TRY(grid_barrier(c));  // MPI_Barrier(lu_comm) before t1 (conflux_opt.hpp:531)
     cudaEvent_t e0, e1;
     CFLX_CUDA(cudaEventCreate(&e0));
@@ -749,7 +816,7 @@ int cflx_lu_factor(cflx_lu* lu, double* ms_out) {
     }
     lu->ev_used.assign(2 * lu->Nt, 0);
     {
-        cudaStream_t side = lu->profiling ? nullptr : lu->side;
+        cudaStream_t side = (lu->prof_mode == 1) ? nullptr : lu->side;
         if (side) {
             CFLX_CUDA(cudaEventRecord(lu->ev_fork, s));
             CFLX_CUDA(cudaStreamWaitEvent(side, lu->ev_fork, 0));
@@ -777,6 +844,19 @@ int cflx_lu_factor(cflx_lu* lu, double* ms_out) {
     cudaEventDestroy(e1);
     CFLX_CUDA(cudaGetLastError());
     if (ms_out) *ms_out = ms;
+    if (lu->prof_mode == 2) {  // resolve the timeline: every event has completed (e1 was synchronised, the side stream joined)
+        if (lu->side) cudaStreamSynchronize(lu->side);
+        for (const auto& r : lu->tl_recs) {
+            float g = 0;
+            if (cudaEventElapsedTime(&g, lu->tl_pool[r.ev], lu->tl_pool[r.ev + 1]) == cudaSuccess) {
+                lu->region_ms[r.side][r.region] += g;
+                lu->region_cnt[r.side][r.region]++;
+                lu->phase_ms[region_phase(r.region)] += g;
+            } else {
+                cudaGetLastError();
+            }
+        }
+    }
     if (lu->time_gemm) {
         for (int i = 0; i < 2 * lu->Nt; ++i) {
             if (!lu->ev_used[i]) continue;
@@ -866,9 +946,31 @@ int cflx_lu_launch_count(cflx_lu* lu, int64_t* count_out, int reset) {
     if (reset) lu->launches = 0;
     return CFLX_OK;
 }
-int cflx_lu_set_profiling(cflx_lu* lu, int enabled) {
+int cflx_lu_set_profiling(cflx_lu* lu, int mode) {  // 0 off, 1 serialising phase timers, 2 non-serialising timeline
+    if (!lu || mode < 0 || mode > 2) return CFLX_ERR_ARG;
+    lu->prof_mode = mode;
+    return CFLX_OK;
+}
+// JSON text {"main": {region: [ms, count], ...}, "side": {...}} of the last profiled cflx_lu_factor; region names are the
+// reference's semiprof regions.  Returns the length needed (incl. the terminator) when buf is too small.
+int cflx_lu_timeline(cflx_lu* lu, char* buf, int buf_len) {
     if (!lu) return CFLX_ERR_ARG;
-    lu->profiling = enabled != 0;
+    std::string o = "{";
+    for (int sd = 0; sd < 2; ++sd) {
+        o += sd ? ", \"side\": {" : "\"main\": {";
+        bool first = true;
+        for (int r = 0; r < RG_COUNT; ++r) {
+            if (!lu->region_cnt[sd][r]) continue;
+            char tmp[160];
+            snprintf(tmp, sizeof(tmp), "%s\"%s\": [%.4f, %d]", first ? "" : ", ", region_name(r), lu->region_ms[sd][r], lu->region_cnt[sd][r]);
+            o += tmp;
+            first = false;
+        }
+        o += "}";
+    }
+    o += "}";
+    if (!buf || buf_len <= (int)o.size()) return (int)o.size() + 1;
+    std::memcpy(buf, o.c_str(), o.size() + 1);
     return CFLX_OK;
 }
 int cflx_lu_phase_ms(cflx_lu* lu, double* ms_out) {

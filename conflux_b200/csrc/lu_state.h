@@ -34,6 +34,26 @@ struct SubComm {
 
 enum Phase { PH_PANEL = 0, PH_TOURN, PH_MOVES, PH_REDUCE, PH_TRSM, PH_GEMM, PH_STORE, PH_OTHER, PH_COUNT };
 
+// Profiling regions, named like the reference's semiprof regions (PE(...) in conflux_opt.hpp; profiler.hpp:5-19) so
+// that an Nsight Systems timeline (NVTX ranges) or cflx_lu_timeline() reads like the reference's profiler summary.
+enum Region {
+    RG_init = 0, RG_step0_copy, RG_step0_reduce, RG_step1_A10copy, RG_step1_lup, RG_step1_rowpermute, RG_step1_pivoting,
+    RG_step1_A00Buff_bcast, RG_step2_pushingpivots, RG_step2_reduce, RG_step4_reshuffling, RG_step4_dtrsm, RG_step4_comm,
+    RG_step5_dtrsm, RG_step5_comm, RG_step6_dgemm, RG_storingresults, RG_COUNT
+};
+inline const char* region_name(int r) {
+    static const char* n[RG_COUNT] = {"init", "step0_copy", "step0_reduce", "step1_A10copy", "step1_lup", "step1_rowpermute",
+                                      "step1_pivoting", "step1_A00Buff_bcast", "step2_pushingpivots", "step2_reduce",
+                                      "step4_reshuffling", "step4_dtrsm", "step4_comm", "step5_dtrsm", "step5_comm",
+                                      "step6_dgemm", "storingresults"};
+    return n[r];
+}
+inline int region_phase(int r) {
+    static const int p[RG_COUNT] = {PH_OTHER, PH_PANEL, PH_PANEL, PH_PANEL, PH_PANEL, PH_PANEL, PH_TOURN, PH_TOURN, PH_MOVES,
+                                    PH_REDUCE, PH_MOVES, PH_TRSM, PH_REDUCE, PH_TRSM, PH_REDUCE, PH_GEMM, PH_STORE};
+    return p[r];
+}
+
 template <class T>
 inline int dmalloc(T** p, size_t n) {
     CFLX_CUDA(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T) + 4096));  // tail pad: bulk copies may over-read
@@ -56,13 +76,22 @@ struct cflx_lu {
         *tagsS = nullptr, *hist = nullptr, *plan_mem = nullptr, *idx_buf = nullptr;
     cflx::MovePlan plan{};
     cflx::PanelWorkspace pws{};
+    cflx::OzakiWorkspace oz{};   // digit planes of the int8 tcgen05 trailing update (CFLX_GEMM=ozaki)
+    bool use_ozaki = false;
     int64_t ldp_max = 0;
     int* h_npiv = nullptr;  // pinned
     std::vector<int> h_hist;
-    bool have_input = false, factored = false, profiling = false, time_gemm = false;
+    bool have_input = false, factored = false, time_gemm = false;
     double gemm_ms = 0, gemm_flops = 0;
     int64_t launches = 0;
     double phase_ms[cflx::PH_COUNT] = {0};
+    // non-serialising timeline (profiling mode 2): event pairs recorded on the launching stream, resolved after the run
+    struct TlRec { int region, side, ev; };
+    std::vector<cudaEvent_t> tl_pool;
+    std::vector<TlRec> tl_recs;
+    double region_ms[2][cflx::RG_COUNT] = {{0}};   // [main / side stream][region]
+    int region_cnt[2][cflx::RG_COUNT] = {{0}};
+    int prof_mode = 0;                              // 0 off, 1 serialising phase timers, 2 timeline
     std::vector<cudaEvent_t> ev;
     std::vector<char> ev_used;
     cudaStream_t side = nullptr;  // high-priority look-ahead stream (null: no overlap)

@@ -1,0 +1,501 @@
+// conflux_b200/csrc/ozaki.cu -- the trailing update  C -= L * U  on the 5th-generation tensor cores (tcgen05, int8).
+//
+// Replaces cblas_dgemm at /root/reference/src/conflux/lu/conflux_opt.hpp:1628-1632 on the path selected by
+// CFLX_GEMM=ozaki (gemm.cu's DMMA kernel stays the anchor and serves the TRSM sweeps).  tcgen05.mma has no f64 kind, so
+// FP64 accuracy is recovered with error-free slicing (Ozaki scheme):
+//   * every row m of L and every column n of U gets ONE power-of-two scale 2^ea[m] / 2^eb[n] (its largest magnitude);
+//   * the scaled entries are cut into S = 8 signed digits (first 6 bits, then 7 bits each, round-to-nearest so every
+//     digit fits [-64, 64]): x = 2^(e-6) * sum_s d_s 2^(-7s), exact to 55 bits relative to the row/column maximum;
+//   * every digit-plane product  sum_k da_s[m][k] * db_t[k][n]  is an EXACT int8 x int8 -> int32 GEMM
+//     (tcgen05.mma.kind::i8, accumulators in tensor memory); the planes with s + t = g share one accumulator (their
+//     weight 2^(-7g) is the same; at most 8 products of <= 2^12 * K, K <= 512: < 2^25), only g <= 7 is kept (36 MMAs);
+//   * the epilogue recombines  sum_g 2^(-7g) acc_g  in FP64, applies 2^(ea+eb-12) and subtracts from C in place.
+// The neglected planes (g >= 8) are below 2^-56 of |row max| * |column max| per term: the same order as the rounding of
+// a native FP64 dot product of that length (tools/ozaki_study.py: residual and pivots unchanged at 8 slices).
+//
+// Kernel structure (one CTA per SM, 384 threads, all 512 TMEM columns):
+//   warp 0     TMA producer: digit planes are K-major int8 ([plane][row][K], 128-byte swizzled boxes of 128 k) fetched
+//              with cp.async.bulk.tensor.3d through two tensor maps; per 128-k chunk the 8 B planes stay resident
+//              (double-buffered set) while the 8 A planes stream through a 3-slot ring: every plane chunk is loaded
+//              exactly once per tile;
+//   warp 1     MMA issuer: one thread, UMMA 128 x (64..256) x 32 (up to four B planes per instruction), smem descriptors (SWIZZLE_128B, K-major), tcgen05.commit
+//              onto the mbarriers that free operand slots and publish finished accumulators;
+//   warp 2     TMEM allocation / release;
+//   warps 4-11 epilogue: tcgen05.ld 32x32b (lane = row), int32 -> FP64 recombination in registers, then a per-warp
+//              shared-memory patch turns "thread = row" into coalesced 64-byte row segments for the C read-modify-write.
+// The 8 accumulators double as the pipeline between MMA and epilogue: group g of the next tile starts as soon as the
+// epilogue has drained group g of the current one.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cflx {
+
+namespace {
+constexpr int OZ_S = 8;           // digit planes per operand
+constexpr int OZ_BM = 128, OZ_BN = 64, OZ_KC = 128;  // CTA tile, k-chunk (bytes = int8 elements)
+constexpr int OZ_A_SLOTS = 3;
+constexpr int OZ_A_BYTES = OZ_BM * OZ_KC, OZ_B_BYTES = OZ_BN * OZ_KC;
+constexpr int OZ_THREADS = 384;
+constexpr int OZ_PATCH_LD = 10;   // doubles per patch row (8 + 2 padding)
+constexpr size_t OZ_SMEM_OPERANDS = (size_t)2 * OZ_S * OZ_B_BYTES + (size_t)OZ_A_SLOTS * OZ_A_BYTES;
+constexpr size_t OZ_SMEM = 1024 /*alignment slack*/ + OZ_SMEM_OPERANDS + 8 * 32 * OZ_PATCH_LD * sizeof(double) + 512 /*barriers*/;
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D(tmem) (+)= A(smem desc) * B(smem desc), int8 x int8 -> int32
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// shared-memory matrix descriptor of a K-major, 128-byte-swizzled operand tile (rows of 128 bytes, 8-row groups 1024 B
+// apart): start address >> 4 | SBO = 1024 >> 4 at bit 32 | version 1 at bit 46 | SWIZZLE_128B (2) at bit 61
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor, kind::i8: D = S32 (2 at bit 4), A = B = signed int8 (1 at bits 7 / 10), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t oz_idesc(int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+}
+
+// coherent 16-byte load of C without a memory clobber: free to be scheduled ahead of stores to OTHER elements (every
+// element is read once, by the thread that later writes it), see gemm.cu
+__device__ __forceinline__ double2 ld_c2(const double* p) {
+    double2 v;
+    asm("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void l2_prefetch_256(const void* p) {  // 16-byte aligned, 256 bytes
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], 256;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ double pow2i(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }  // |e| < 1022
+
+struct OzArgs {
+    int M, N, K;           // C is M x N, K = contraction length (multiple of 128)
+    int b_row0;            // first row of the B planes that belongs to column 0 of this C window
+    double* C;             // in place: C -= A^T-planes * B-planes
+    int64_t ldc;
+    const int* ea;         // [M]   row exponents of A
+    const int* eb;         // [...] column exponents of B, indexed like the B planes (b_row0 + n)
+    int tiles_m, tiles_n;
+    long long* dbg;        // optional [16] cycle counters of CTA 0: see cflx_dbg_ozaki_cycles
+};
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, OzArgs g) {
+    extern __shared__ unsigned char oz_smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)oz_smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* sB = base;                                        // [2][8][64 x 128 B]
+    unsigned char* sA = base + (size_t)2 * OZ_S * OZ_B_BYTES;         // [3][128 x 128 B]
+    double* patch = reinterpret_cast<double*>(base + OZ_SMEM_OPERANDS);  // [8 warps][32][OZ_PATCH_LD]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(patch + 8 * 32 * OZ_PATCH_LD);
+    uint64_t* fullB = bars;                 // [2][8]
+    uint64_t* emptyB = bars + 16;           // [2][8]
+    uint64_t* fullA = bars + 32;            // [3]
+    uint64_t* emptyA = bars + 35;           // [3]
+    uint64_t* tfull = bars + 38;            // [8]
+    uint64_t* tempty = bars + 46;           // [8]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 54);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = g.tiles_m * g.tiles_n;
+    const int KC = g.K / OZ_KC;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 16; ++i) {
+            mbar_init(&fullB[i], 1);
+            mbar_init(&emptyB[i], 1);
+        }
+        for (int i = 0; i < OZ_A_SLOTS; ++i) {
+            mbar_init(&fullA[i], 1);
+            mbar_init(&emptyA[i], 1);
+        }
+        for (int i = 0; i < OZ_S; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 8);  // one arrival per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    long long tm[4] = {0, 0, 0, 0};
+    long long tc0 = 0;
+#define OZ_T0() if (g.dbg) tc0 = clock64();
+#define OZ_T1(i) if (g.dbg) tm[i] += clock64() - tc0;
+    const long long t_begin = g.dbg ? clock64() : 0;
+    if (warp == 0) {
+        // ================================================================== TMA producer
+        uint32_t q = 0, acnt = 0;  // k-chunks and A planes loaded so far by this CTA
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int m0 = (tile / g.tiles_n) * OZ_BM, n0 = (tile % g.tiles_n) * OZ_BN;
+            for (int kc = 0; kc < KC; ++kc, ++q) {
+                const int set = q & 1;
+                const uint32_t useB = q >> 1;
+                for (int t = 0; t < OZ_S; ++t) {
+                    OZ_T0() mbar_wait(&emptyB[set * 8 + t], (useB & 1) ^ 1); OZ_T1(0)
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&fullB[set * 8 + t], OZ_B_BYTES);
+                        tma_load_3d(sB + (size_t)(set * 8 + t) * OZ_B_BYTES, &mapB, kc * OZ_KC, g.b_row0 + n0, t, &fullB[set * 8 + t]);
+                    }
+                }
+                for (int s = 0; s < OZ_S; ++s, ++acnt) {
+                    const int slot = acnt % OZ_A_SLOTS;
+                    const uint32_t useA = acnt / OZ_A_SLOTS;
+                    OZ_T0() mbar_wait(&emptyA[slot], (useA & 1) ^ 1); OZ_T1(1)
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&fullA[slot], OZ_A_BYTES);
+                        tma_load_3d(sA + (size_t)slot * OZ_A_BYTES, &mapA, kc * OZ_KC, m0, s, &fullA[slot]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================== MMA issuer
+        uint32_t q = 0, acnt = 0, it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            for (int kc = 0; kc < KC; ++kc, ++q) {
+                const int set = q & 1;
+                const uint32_t useB = q >> 1;
+                for (int s = 0; s < OZ_S; ++s, ++acnt) {
+                    const int slot = acnt % OZ_A_SLOTS;
+                    OZ_T0() mbar_wait(&fullA[slot], (acnt / OZ_A_SLOTS) & 1); OZ_T1(0)
+                    const uint64_t adesc = smem_desc_sw128(smem_u32(sA + (size_t)slot * OZ_A_BYTES));
+                    if (s == 0) {  // row 0 touches every B plane and (first k chunk) every accumulator
+                        for (int t = 0; t < OZ_S; ++t) {
+                            OZ_T0() mbar_wait(&fullB[set * 8 + t], useB & 1); OZ_T1(1)
+                            OZ_T0() if (kc == 0) mbar_wait(&tempty[t], (it & 1) ^ 1); OZ_T1(2)  // epilogue drained this accumulator
+                        }
+                    }
+                    tc_fence_after();
+                    if (lane == 0) {
+                        // The B planes t, t+1, ... of a set are contiguous 64-row tiles and their accumulators (groups s+t,
+                        // s+t+1, ...) are contiguous 64-column blocks of tensor memory: up to four planes go through ONE
+                        // UMMA of N = 64 * planes, so A_s is read from shared memory once per four products.
+                        for (int t = 0; t < OZ_S - s; t += 4) {
+                            const int np = min(4, OZ_S - s - t);
+                            const uint64_t bdesc = smem_desc_sw128(smem_u32(sB + (size_t)(set * 8 + t) * OZ_B_BYTES));
+                            const uint32_t d = tmem_base + (uint32_t)(s + t) * OZ_BN;
+                            const uint32_t idesc = oz_idesc(np * OZ_BN);
+#pragma unroll
+                            for (int k = 0; k < OZ_KC / 32; ++k)  // +32 bytes along K inside the swizzle atom: +2 in the descriptor
+                                umma_i8(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > 0 || s > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        tc_commit(&emptyA[slot]);                         // plane s of A is consumed
+                        tc_commit(&emptyB[set * 8 + (OZ_S - 1 - s)]);     // plane 7-s of B was used for the last time
+                        if (kc == KC - 1) tc_commit(&tfull[s]);           // groups <= s are complete
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================================================== epilogue (8 warps)
+        const int ew = warp - 4;
+        const int lq = warp & 3;             // TMEM lane quadrant this warp may access
+        const int ch = ew >> 2;              // column half of the 64-wide tile
+        double* my_patch = patch + (size_t)ew * 32 * OZ_PATCH_LD;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int m0 = (tile / g.tiles_n) * OZ_BM, n0 = (tile % g.tiles_n) * OZ_BN;
+            {   // pull my row's 256-byte segment of the C tile into L2 now; it is needed after the 8 accumulators
+                const int prow = m0 + lq * 32 + lane, pcol = n0 + ch * 32;
+                if (prow < g.M && pcol + 32 <= g.N) l2_prefetch_256(g.C + (int64_t)prow * g.ldc + pcol);
+            }
+            double sum[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[j] = 0.0;
+            double w = 1.0;
+#pragma unroll 1
+            for (int grp = 0; grp < OZ_S; ++grp) {
+                OZ_T0() mbar_wait(&tfull[grp], it & 1); OZ_T1(0)
+                OZ_T0()
+                tc_fence_after();
+                int acc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(grp * OZ_BN + ch * 32), acc);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[grp]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    // exact int32 -> double without the conversion pipe: 2^52 + 2^31 + x, then subtract the bias
+                    const double x = __hiloint2double(0x43300000, acc[j] ^ 0x80000000) - 4503601774854144.0;
+                    sum[j] = fma(x, w, sum[j]);
+                }
+                w *= 0.0078125;  // 2^-7
+                OZ_T1(1)
+            }
+            OZ_T0()
+            // ---- C -= sum * 2^(ea + eb - 12), coalesced through the warp's patch: 8 columns at a time.  The C rows were
+            // pulled into L2 by the bulk prefetch issued at the top of the tile, so these loads see L2 latency only; the
+            // four loads of a column group are issued before its four stores.
+            const int row = m0 + lq * 32 + lane;
+            const double srow = (row < g.M) ? pow2i(g.ea[row] - 12) : 0.0;
+            const int colbase = n0 + ch * 32;
+            const int cp = lane & 3;                           // column pair inside the 8-column group
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+                const int col = colbase + c8 * 8 + 2 * cp;
+                const bool cok = col < g.N;
+                double2 cv[4];
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int r = m0 + lq * 32 + rr * 8 + (lane >> 2);
+                    cv[rr] = make_double2(0.0, 0.0);
+                    if (cok && r < g.M) cv[rr] = ld_c2(g.C + (int64_t)r * g.ldc + col);
+                }
+                double s0 = 0.0, s1 = 0.0;
+                if (cok) {
+                    s0 = pow2i(g.eb[g.b_row0 + col]);
+                    s1 = pow2i(g.eb[g.b_row0 + col + 1]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) my_patch[lane * OZ_PATCH_LD + j] = sum[c8 * 8 + j] * srow;
+                __syncwarp();
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int lr = rr * 8 + (lane >> 2);
+                    const int r = m0 + lq * 32 + lr;
+                    if (cok && r < g.M) {
+                        double2 c = cv[rr];
+                        c.x -= my_patch[lr * OZ_PATCH_LD + 2 * cp] * s0;
+                        c.y -= my_patch[lr * OZ_PATCH_LD + 2 * cp + 1] * s1;
+                        *reinterpret_cast<double2*>(g.C + (int64_t)r * g.ldc + col) = c;
+                    }
+                }
+            }
+            OZ_T1(2)
+        }
+    }
+    if (g.dbg && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 4)) {
+        const int o = warp == 0 ? 0 : (warp == 1 ? 4 : 8);
+        for (int i = 0; i < 3; ++i) g.dbg[o + i] = tm[i];
+        g.dbg[o + 3] = clock64() - t_begin;
+    }
+#undef OZ_T0
+#undef OZ_T1
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------- digit planes
+// src[k][o] (K x ld doubles, o = row of L / column of U) -> planes[s][o0 + o][k] int8 (K contiguous), exps[o0 + o].
+// One CTA per 32 outer indices: pass 1 = largest magnitude per outer index, pass 2 = digits, transposed through smem.
+constexpr int OZ_SPLIT_OUT = 32;
+__global__ void __launch_bounds__(256) ozaki_split_kernel(const double* __restrict__ src, int64_t ld, int n_outer, int K,
+                                                          int8_t* __restrict__ planes, int64_t plane_stride, int o0,
+                                                          int* __restrict__ exps) {
+    constexpr int PITCH = OZ_KC + 4;  // bytes per smem row: 33 words, conflict-free byte scatter
+    __shared__ __align__(16) unsigned char tile[OZ_S][OZ_SPLIT_OUT][PITCH];
+    __shared__ double red[8][OZ_SPLIT_OUT];
+    __shared__ int s_exp[OZ_SPLIT_OUT];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int o = blockIdx.x * OZ_SPLIT_OUT + tx;
+    const bool valid = o < n_outer;
+    double mx = 0.0;
+    if (valid)
+        for (int k = ty; k < K; k += 8) mx = fmax(mx, fabs(src[(int64_t)k * ld + o]));
+    red[ty][tx] = mx;
+    __syncthreads();
+    if (ty == 0) {
+#pragma unroll
+        for (int i = 1; i < 8; ++i) mx = fmax(mx, red[i][tx]);
+        int e = 0;
+        if (mx > 0.0) frexp(mx, &e);  // mx = f * 2^e, f in [0.5, 1): |x| * 2^-e < 1 for the whole row
+        s_exp[tx] = e;
+        if (valid) exps[o0 + o] = e;
+    }
+    __syncthreads();
+    const double inv = pow2i(-s_exp[tx]);
+    for (int k0 = 0; k0 < K; k0 += OZ_KC) {
+        for (int kk = ty; kk < OZ_KC; kk += 8) {
+            double r = valid ? src[(int64_t)(k0 + kk) * ld + o] * inv : 0.0;
+            r *= 64.0;  // first digit: 6 bits
+#pragma unroll
+            for (int s = 0; s < OZ_S; ++s) {
+                const double d = rint(r);
+                tile[s][tx][kk] = (unsigned char)(signed char)(int)d;
+                r = (r - d) * 128.0;
+            }
+        }
+        __syncthreads();
+        // write-out: plane s, outer row, 128 contiguous bytes = 8 x 16 B
+        for (int e = threadIdx.x; e < OZ_S * OZ_SPLIT_OUT * 8; e += 256) {
+            const int s = e / (OZ_SPLIT_OUT * 8), rowi = (e / 8) % OZ_SPLIT_OUT, c16 = e % 8;
+            const int oo = blockIdx.x * OZ_SPLIT_OUT + rowi;
+            if (oo < n_outer) {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(&tile[s][rowi][c16 * 16]);
+                uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(planes + (int64_t)s * plane_stride + (int64_t)(o0 + oo) * K + k0 + c16 * 16) = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && p) fn = (EncodeTiledFn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+// planes: [OZ_S][cap_rows][K] int8; box = 128 bytes of k x box_rows rows of one plane, 128-byte swizzle
+int make_plane_map(CUtensorMap* map, const int8_t* planes, int K, int cap_rows, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_last_error("cuTensorMapEncodeTiled is not available from the driver");
+        return CFLX_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)cap_rows, (cuuint64_t)OZ_S};
+    cuuint64_t strides[2] = {(cuuint64_t)K, (cuuint64_t)K * (cuuint64_t)cap_rows};
+    cuuint32_t box[3] = {(cuuint32_t)OZ_KC, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)planes, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed (%d) for K=%d rows=%d", (int)r, K, cap_rows);
+        return CFLX_ERR_CUDA;
+    }
+    return CFLX_OK;
+}
+}  // namespace
+
+struct OzakiWorkspace::Maps {
+    CUtensorMap a, b;
+};
+
+int ozaki_workspace_create(OzakiWorkspace* ws, int max_rows, int max_cols, int K) {
+    *ws = OzakiWorkspace{};
+    if (K <= 0 || K % OZ_KC != 0 || K > 512) {
+        set_last_error("ozaki: contraction length %d unsupported (multiple of 128, <= 512)", K);
+        return CFLX_ERR_UNSUPPORTED;
+    }
+    ws->K = K;
+    ws->cap_a = (int)round_up(max_rows, OZ_BM);
+    ws->cap_b = (int)round_up(max_cols, OZ_BN);
+    CFLX_CUDA(cudaMalloc((void**)&ws->planesA, (size_t)OZ_S * ws->cap_a * K));
+    CFLX_CUDA(cudaMalloc((void**)&ws->planesB, (size_t)OZ_S * ws->cap_b * K));
+    CFLX_CUDA(cudaMemset(ws->planesA, 0, (size_t)OZ_S * ws->cap_a * K));
+    CFLX_CUDA(cudaMemset(ws->planesB, 0, (size_t)OZ_S * ws->cap_b * K));
+    CFLX_CUDA(cudaMalloc((void**)&ws->ea, sizeof(int) * ws->cap_a));
+    CFLX_CUDA(cudaMalloc((void**)&ws->eb, sizeof(int) * ws->cap_b));
+    CFLX_CUDA(cudaMemset(ws->ea, 0, sizeof(int) * ws->cap_a));
+    CFLX_CUDA(cudaMemset(ws->eb, 0, sizeof(int) * ws->cap_b));
+    if (getenv("CFLX_OZAKI_DBG")) {
+        CFLX_CUDA(cudaMalloc((void**)&ws->dbg, sizeof(long long) * 16));
+        CFLX_CUDA(cudaMemset(ws->dbg, 0, sizeof(long long) * 16));
+    }
+    ws->maps = new OzakiWorkspace::Maps;
+    CFLX_TRY(make_plane_map(&ws->maps->a, ws->planesA, K, ws->cap_a, OZ_BM));
+    CFLX_TRY(make_plane_map(&ws->maps->b, ws->planesB, K, ws->cap_b, OZ_BN));
+    static PerDeviceMax cfg;
+    if (cfg.raise(OZ_SMEM))
+        CFLX_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
+    int dev = 0;
+    CFLX_CUDA(cudaGetDevice(&dev));
+    CFLX_CUDA(cudaDeviceGetAttribute(&ws->sms, cudaDevAttrMultiProcessorCount, dev));
+    return CFLX_OK;
+}
+void ozaki_workspace_destroy(OzakiWorkspace* ws) {
+    cudaFree(ws->planesA);
+    cudaFree(ws->planesB);
+    cudaFree(ws->ea);
+    cudaFree(ws->eb);
+    cudaFree(ws->dbg);
+    delete ws->maps;
+    *ws = OzakiWorkspace{};
+}
+
+// digit planes of rows [0, n) of L^T (LT[k][row], ld) -> A planes
+int ozaki_split_a(OzakiWorkspace* ws, const double* LT, int64_t ld, int n, cudaStream_t s) {
+    if (n <= 0) return CFLX_OK;
+    if (n > ws->cap_a) return CFLX_ERR_ARG;
+    ozaki_split_kernel<<<(n + OZ_SPLIT_OUT - 1) / OZ_SPLIT_OUT, 256, 0, s>>>(LT, ld, n, ws->K, ws->planesA, (int64_t)ws->cap_a * ws->K, 0, ws->ea);
+    CFLX_CUDA(cudaGetLastError());
+    return CFLX_OK;
+}
+// digit planes of columns [col0, col0 + n) of U (U[k][col], ld) -> B planes, rows col0..
+int ozaki_split_b(OzakiWorkspace* ws, const double* U, int64_t ld, int col0, int n, cudaStream_t s) {
+    if (n <= 0) return CFLX_OK;
+    if (col0 < 0 || col0 + n > ws->cap_b) return CFLX_ERR_ARG;
+    ozaki_split_kernel<<<(n + OZ_SPLIT_OUT - 1) / OZ_SPLIT_OUT, 256, 0, s>>>(U + col0, ld, n, ws->K, ws->planesB, (int64_t)ws->cap_b * ws->K, col0, ws->eb);
+    CFLX_CUDA(cudaGetLastError());
+    return CFLX_OK;
+}
+// C[0..M) x [0..N) -= (rows 0..M of the A planes) * (rows col0..col0+N of the B planes)
+int launch_ozaki_gemm(OzakiWorkspace* ws, int M, int N, int col0, double* C, int64_t ldc, int max_ctas, cudaStream_t s) {
+    if (M <= 0 || N <= 0) return CFLX_OK;
+    if ((N & 1) || (ldc & 1) || col0 < 0 || M > ws->cap_a || col0 + N > ws->cap_b) {
+        set_last_error("ozaki_gemm: unsupported window M=%d N=%d col0=%d ldc=%lld", M, N, col0, (long long)ldc);
+        return CFLX_ERR_UNSUPPORTED;
+    }
+    OzArgs g{};
+    g.M = M; g.N = N; g.K = ws->K;
+    g.b_row0 = col0;
+    g.C = C; g.ldc = ldc;
+    g.ea = ws->ea; g.eb = ws->eb;
+    g.tiles_m = (M + OZ_BM - 1) / OZ_BM;
+    g.tiles_n = (N + OZ_BN - 1) / OZ_BN;
+    g.dbg = ws->dbg;
+    int grid = g.tiles_m * g.tiles_n;
+    int cap = ws->sms;
+    if (max_ctas > 0 && max_ctas < cap) cap = max_ctas;
+    if (grid > cap) grid = cap;
+    ozaki_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM, s>>>(ws->maps->a, ws->maps->b, g);
+    CFLX_CUDA(cudaGetLastError());
+    return CFLX_OK;
+}
+
+}  // namespace cflx

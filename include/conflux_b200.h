@@ -93,8 +93,15 @@ int cflx_lu_residual(cflx_lu*, double* rel_out);
 int cflx_lu_launch_count(cflx_lu*, int64_t* count_out, int reset);
 /* per-phase device time of the last cflx_lu_factor when profiling was enabled: ms_out[8] =
  * {panel, tournament+bcast, row moves, reduce+gather, trsm, gemm, stores, other} */
-int cflx_lu_set_profiling(cflx_lu*, int enabled);
+/* mode 0 off; 1 serialising timers (per-phase device time without overlap); 2 non-serialising timeline: CUDA event
+ * pairs on the launching streams, resolved after the run -- the timeline of the real, overlapped execution.  Every region
+ * is also an NVTX range named like the reference's semiprof regions (src/conflux/lu/profiler.hpp:5-19: step0_copy,
+ * step1_lup, step2_pushingpivots, step4_dtrsm, step6_dgemm, ...). */
+int cflx_lu_set_profiling(cflx_lu*, int mode);
 int cflx_lu_phase_ms(cflx_lu*, double* ms_out);
+/* JSON text {"main": {"step6_dgemm": [ms, count], ...}, "side": {...}} of the last profiled cflx_lu_factor (main stream /
+ * look-ahead stream).  Returns 0, or the buffer length needed when buf is NULL or too small. */
+int cflx_lu_timeline(cflx_lu*, char* buf, int buf_len);
 /* CUDA-event timing of the dominant kernel (the trailing-update DGEMM launches of the last cflx_lu_factor, events
  * recorded on the launching stream): summed device ms and the algorithmic flops 2*m*n*k of those launches */
 int cflx_lu_set_kernel_timing(cflx_lu*, int enabled);
@@ -110,6 +117,12 @@ int cflx_dbg_panel(int n, int v, const double* panel, int* perm_out, double* A00
                    double* ms_out);
 /* X = B * U^-1 (right, upper, non-unit; B n x v) and Y = L^-1 * R (left, lower, unit; R v x n), A00 = L\U packed */
 int cflx_dbg_trsm(int n, int v, const double* A00, const double* B, double* X_out, const double* R, double* Y_out);
+/* D = C - AT^T * B on the int8 tcgen05 path (error-free digit planes, ozaki.cu); K % 128 == 0, N even.  Optional test
+ * outputs: digit planes [8][M][K] / [8][N][K], exponents [M] / [N].  ms_out / split_ms_out: mean device time of the GEMM
+ * kernel / of the two digit-plane kernels. */
+int cflx_dbg_ozaki_gemm(int M, int N, int K, const double* AT, const double* B, const double* C, double* D,
+                        signed char* planesA_out, signed char* planesB_out, int* ea_out, int* eb_out, int reps,
+                        double* ms_out, double* split_ms_out);
 /* plan_moves + push_phase1..3 + gri bookkeeping on one rank: the npiv pivot rows (local indices >= fnpr, tournament
  * order) are pushed to rows [fnpr, fnpr+npiv) exactly like push_pivots_up (conflux_opt.hpp:176-218, tests/unit/
  * test_utils.cpp:8-84).  n_cols even.  gri_out[n_rows] = new row -> old row, a01_out[npiv*n_cols] = extracted rows. */
