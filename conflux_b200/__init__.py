@@ -273,6 +273,13 @@ class dbg:
         return A, gri, a01[:len(piv)]
 
     @staticmethod
+    def umma_peak(which, n):
+        """tera-MACs/s of back-to-back tcgen05.mma 128 x n x 32B-K: which 0 = kind::i8, 1 = kind::f16 (bf16)."""
+        t = ctypes.c_double()
+        check(lib().cflx_dbg_umma_peak(int(which), int(n), ctypes.byref(t)), "dbg_umma_peak")
+        return t.value
+
+    @staticmethod
     def fp64_peak_ex(which):
         """(burst, sustained) TFLOP/s of the DMMA (0) / DFMA (1) pipe."""
         a, b = ctypes.c_double(), ctypes.c_double()

@@ -214,7 +214,9 @@ int cflx_dbg_panel(int n, int v, const double* panel, int* perm_out, double* A00
 int cflx_dbg_trsm(int n, int v, const double* A00, const double* B, double* X_out, const double* R, double* Y_out) {
     CFLX_TRY(check_device());
     if (n <= 0 || v <= 0 || v % 4 != 0) return CFLX_ERR_ARG;
-    int nb = (v % 64 == 0) ? 64 : (v <= 128 ? v : (v % 32 == 0 ? 32 : (v % 16 == 0 ? 16 : 0)));
+    int nb = 0;
+    for (int c : {128, 64, 32, 16, 8, 4})
+        if (!nb && v % c == 0) nb = c;
     if (nb == 0) return CFLX_ERR_UNSUPPORTED;
     const int64_t ld = round_up(n, 2);
     std::vector<double> A00T((size_t)v * v), BT((size_t)v * ld, 0.0), RT((size_t)v * ld, 0.0);
@@ -372,6 +374,14 @@ int cflx_dbg_ozaki_gemm(int M, int N, int K, const double* AT, const double* B, 
     if (ms_out) *ms_out = ms / reps;
     if (split_ms_out) *split_ms_out = ms_split / reps;
     return rc;
+}
+
+// raw tensor-pipe rate of back-to-back tcgen05.mma 128 x n x 32-byte-K instructions (one CTA per SM, operands resident in
+// shared memory): which = 0 kind::i8, 1 kind::f16 (bf16).  Returns tera-MACs per second (x2 = TOP/s / TFLOP/s).
+int cflx_dbg_umma_peak(int which, int n, double* tmacs_out) {
+    CFLX_TRY(check_device());
+    if (!tmacs_out) return CFLX_ERR_ARG;
+    return umma_peak_probe(n, which, tmacs_out);
 }
 
 }  // extern "C"

@@ -71,8 +71,8 @@ bool fixed_input_matrix(int n, std::vector<double>* out) {
     }
     return false;
 }
-int pick_nb(int v) {  // block size of the diagonal inverses / TRSM sweeps (template instances: 64, 32, 16, 8, 4)
-    for (int nb : {64, 32, 16, 8, 4})
+int pick_nb(int v) {  // block size of the diagonal inverses / TRSM sweeps (template instances: 128, 64, 32, 16, 8, 4)
+    for (int nb : {128, 64, 32, 16, 8, 4})
         if (v % nb == 0) return nb;
     return 0;
 }

@@ -13,7 +13,7 @@
 // The neglected planes (g >= 8) are below 2^-56 of |row max| * |column max| per term: the same order as the rounding of
 // a native FP64 dot product of that length (tools/ozaki_study.py: residual and pivots unchanged at 8 slices).
 //
-// Kernel structure (one CTA per SM, 384 threads, all 512 TMEM columns):
+// Kernel structure (one CTA per SM, 640 threads, all 512 TMEM columns):
 //   warp 0     TMA producer: digit planes are K-major int8 ([plane][row][K], 128-byte swizzled boxes of 128 k) fetched
 //              with cp.async.bulk.tensor.3d through two tensor maps; per 128-k chunk the 8 B planes stay resident
 //              (double-buffered set) while the 8 A planes stream through a 3-slot ring: every plane chunk is loaded
@@ -21,12 +21,13 @@
 //   warp 1     MMA issuer: one thread, UMMA 128 x (64..256) x 32 (up to four B planes per instruction), smem descriptors (SWIZZLE_128B, K-major), tcgen05.commit
 //              onto the mbarriers that free operand slots and publish finished accumulators;
 //   warp 2     TMEM allocation / release;
-//   warps 4-11 epilogue: tcgen05.ld 32x32b (lane = row), int32 -> FP64 recombination in registers, then a per-warp
+//   warps 4-19 epilogue: tcgen05.ld 32x32b (lane = row), int32 -> FP64 recombination in registers, then a per-warp
 //              shared-memory patch turns "thread = row" into coalesced 64-byte row segments for the C read-modify-write.
 // The 8 accumulators double as the pipeline between MMA and epilogue: group g of the next tile starts as soon as the
 // epilogue has drained group g of the current one.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -40,10 +41,11 @@ constexpr int OZ_S = 8;           // digit planes per operand
 constexpr int OZ_BM = 128, OZ_BN = 64, OZ_KC = 128;  // CTA tile, k-chunk (bytes = int8 elements)
 constexpr int OZ_A_SLOTS = 3;
 constexpr int OZ_A_BYTES = OZ_BM * OZ_KC, OZ_B_BYTES = OZ_BN * OZ_KC;
-constexpr int OZ_THREADS = 384;
+constexpr int OZ_EPI_WARPS = 16;  // 4 per TMEM lane quadrant, 16 columns each
+constexpr int OZ_THREADS = 128 + 32 * OZ_EPI_WARPS;
 constexpr int OZ_PATCH_LD = 10;   // doubles per patch row (8 + 2 padding)
 constexpr size_t OZ_SMEM_OPERANDS = (size_t)2 * OZ_S * OZ_B_BYTES + (size_t)OZ_A_SLOTS * OZ_A_BYTES;
-constexpr size_t OZ_SMEM = 1024 /*alignment slack*/ + OZ_SMEM_OPERANDS + 8 * 32 * OZ_PATCH_LD * sizeof(double) + 512 /*barriers*/;
+constexpr size_t OZ_SMEM = 1024 /*alignment slack*/ + OZ_SMEM_OPERANDS + OZ_EPI_WARPS * 32 * OZ_PATCH_LD * sizeof(double) + 512 /*barriers*/;
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
@@ -67,15 +69,12 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&r)[32]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16]) {  // lane = thread, 16 consecutive columns
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
-          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
-          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -98,8 +97,8 @@ __device__ __forceinline__ double2 ld_c2(const double* p) {
     asm("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
-__device__ __forceinline__ void l2_prefetch_256(const void* p) {  // 16-byte aligned, 256 bytes
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], 256;" ::"l"(p) : "memory");
+__device__ __forceinline__ void l2_prefetch_128(const void* p) {  // 16-byte aligned, 128 bytes
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], 128;" ::"l"(p) : "memory");
 }
 __device__ __forceinline__ double pow2i(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }  // |e| < 1022
 
@@ -120,8 +119,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)oz_smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* sB = base;                                        // [2][8][64 x 128 B]
     unsigned char* sA = base + (size_t)2 * OZ_S * OZ_B_BYTES;         // [3][128 x 128 B]
-    double* patch = reinterpret_cast<double*>(base + OZ_SMEM_OPERANDS);  // [8 warps][32][OZ_PATCH_LD]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(patch + 8 * 32 * OZ_PATCH_LD);
+    double* patch = reinterpret_cast<double*>(base + OZ_SMEM_OPERANDS);  // [epilogue warps][32][OZ_PATCH_LD]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(patch + OZ_EPI_WARPS * 32 * OZ_PATCH_LD);
     uint64_t* fullB = bars;                 // [2][8]
     uint64_t* emptyB = bars + 16;           // [2][8]
     uint64_t* fullA = bars + 32;            // [3]
@@ -145,7 +144,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
         for (int i = 0; i < OZ_S; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 8);  // one arrival per epilogue warp
+            mbar_init(&tempty[i], OZ_EPI_WARPS);  // one arrival per epilogue warp
         }
         fence_barrier_init();
     }
@@ -232,34 +231,46 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             }
         }
     } else if (warp >= 4) {
-        // ================================================================== epilogue (8 warps)
+        // ================================================================== epilogue (16 warps)
         const int ew = warp - 4;
         const int lq = warp & 3;             // TMEM lane quadrant this warp may access
-        const int ch = ew >> 2;              // column half of the 64-wide tile
+        const int cq = ew >> 2;              // 16-column quarter of the 64-wide tile
         double* my_patch = patch + (size_t)ew * 32 * OZ_PATCH_LD;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int m0 = (tile / g.tiles_n) * OZ_BM, n0 = (tile % g.tiles_n) * OZ_BN;
-            {   // pull my row's 256-byte segment of the C tile into L2 now; it is needed after the 8 accumulators
-                const int prow = m0 + lq * 32 + lane, pcol = n0 + ch * 32;
-                if (prow < g.M && pcol + 32 <= g.N) l2_prefetch_256(g.C + (int64_t)prow * g.ldc + pcol);
+            {   // pull my row's 128-byte segment of the C tile into L2 now; it is needed after the 8 accumulators
+                const int prow = m0 + lq * 32 + lane, pcol = n0 + cq * 16;
+                if (prow < g.M && pcol + 16 <= g.N) l2_prefetch_128(g.C + (int64_t)prow * g.ldc + pcol);
             }
-            double sum[32];
+            // scales of my row and of the four column pairs I will store (needed only after the accumulators)
+            const int row = m0 + lq * 32 + lane;
+            const int colbase = n0 + cq * 16;
+            const int cp = lane & 3;                           // column pair inside an 8-column group
+            const double srow = (row < g.M) ? pow2i(g.ea[row] - 12) : 0.0;
+            double sc[2][2];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sum[j] = 0.0;
+            for (int c8 = 0; c8 < 2; ++c8) {
+                const int col = colbase + c8 * 8 + 2 * cp;
+                sc[c8][0] = col < g.N ? pow2i(g.eb[g.b_row0 + col]) : 0.0;
+                sc[c8][1] = col < g.N ? pow2i(g.eb[g.b_row0 + col + 1]) : 0.0;
+            }
+            double sum[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sum[j] = 0.0;
             double w = 1.0;
 #pragma unroll 1
             for (int grp = 0; grp < OZ_S; ++grp) {
                 OZ_T0() mbar_wait(&tfull[grp], it & 1); OZ_T1(0)
                 OZ_T0()
                 tc_fence_after();
-                int acc[32];
-                tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(grp * OZ_BN + ch * 32), acc);
+                int acc[16];
+                tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(grp * OZ_BN + cq * 16), acc);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[grp]);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < 16; ++j) {
                     // exact int32 -> double without the conversion pipe: 2^52 + 2^31 + x, then subtract the bias
                     const double x = __hiloint2double(0x43300000, acc[j] ^ 0x80000000) - 4503601774854144.0;
                     sum[j] = fma(x, w, sum[j]);
@@ -271,12 +282,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             // ---- C -= sum * 2^(ea + eb - 12), coalesced through the warp's patch: 8 columns at a time.  The C rows were
             // pulled into L2 by the bulk prefetch issued at the top of the tile, so these loads see L2 latency only; the
             // four loads of a column group are issued before its four stores.
-            const int row = m0 + lq * 32 + lane;
-            const double srow = (row < g.M) ? pow2i(g.ea[row] - 12) : 0.0;
-            const int colbase = n0 + ch * 32;
-            const int cp = lane & 3;                           // column pair inside the 8-column group
 #pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
+            for (int c8 = 0; c8 < 2; ++c8) {
                 const int col = colbase + c8 * 8 + 2 * cp;
                 const bool cok = col < g.N;
                 double2 cv[4];
@@ -286,11 +293,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                     cv[rr] = make_double2(0.0, 0.0);
                     if (cok && r < g.M) cv[rr] = ld_c2(g.C + (int64_t)r * g.ldc + col);
                 }
-                double s0 = 0.0, s1 = 0.0;
-                if (cok) {
-                    s0 = pow2i(g.eb[g.b_row0 + col]);
-                    s1 = pow2i(g.eb[g.b_row0 + col + 1]);
-                }
+                const double s0 = sc[c8][0], s1 = sc[c8][1];
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 8; ++j) my_patch[lane * OZ_PATCH_LD + j] = sum[c8 * 8 + j] * srow;
@@ -320,6 +323,52 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     tc_fence_before();
     __syncthreads();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------- raw UMMA rate probe
+// Back-to-back tcgen05.mma on one resident shared-memory tile per SM (no TMA, no epilogue): the tensor pipe's own rate
+// for kind::i8 (and kind::f16 for calibration against the bf16 peak in MEASURED_PEAKS.json).
+__global__ void __launch_bounds__(128, 1) umma_peak_kernel(int n, int use_f16, int iters) {
+    extern __shared__ unsigned char pk_smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)pk_smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tslot;
+    for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base)[i] = 0x01010101u * (i & 3);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    fence_proxy_async();
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tslot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = tslot;
+    if (threadIdx.x == 0) {
+        const uint64_t adesc = smem_desc_sw128(smem_u32(base)), bdesc = smem_desc_sw128(smem_u32(base + 16384));
+        // f16 kind: D = F32 (1 at bit 4), A = B = BF16 (1 at bits 7 / 10); i8 kind as in the GEMM
+        const uint32_t idesc = use_f16 ? ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | (8u << 24)) : oz_idesc(n);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (use_f16)
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tb + (uint32_t)((it & 1) * 256)),
+                                 "l"(adesc + 2 * k), "l"(bdesc + 2 * k), "r"(idesc), "r"(1u)
+                                 : "memory");
+                else
+                    umma_i8(tb + (uint32_t)((it & 1) * 256), adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+            }
+        }
+        tc_commit(&bar);
+        mbar_wait(&bar, 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------- digit planes
@@ -456,6 +505,38 @@ void ozaki_workspace_destroy(OzakiWorkspace* ws) {
     cudaFree(ws->dbg);
     delete ws->maps;
     *ws = OzakiWorkspace{};
+}
+
+// Tera-MACs/s of back-to-back UMMA 128 x n x (32 bytes of K) instructions, one CTA per SM: use_f16 = 0 -> kind::i8
+// (32 int8 per instruction), 1 -> kind::f16 on bf16 (16 elements per instruction).
+int umma_peak_probe(int n, int use_f16, double* tmacs_out) {
+    if (n < 16 || n > 256 || n % 16) return CFLX_ERR_ARG;
+    int dev = 0, sms = 0;
+    CFLX_CUDA(cudaGetDevice(&dev));
+    CFLX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t smem = 1024 + 16384 + 32768;
+    CFLX_CUDA(cudaFuncSetAttribute(umma_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1;
+    CFLX_CUDA(cudaEventCreate(&e0));
+    CFLX_CUDA(cudaEventCreate(&e1));
+    const int iters = 20000;
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CFLX_CUDA(cudaEventRecord(e0));
+        umma_peak_kernel<<<sms, 128, smem>>>(n, use_f16, iters);
+        CFLX_CUDA(cudaEventRecord(e1));
+        CFLX_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        CFLX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double kper = use_f16 ? 16.0 : 32.0;
+        const double macs = (double)sms * iters * 4 * 128.0 * n * kper;
+        best = std::max(best, macs / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CFLX_CUDA(cudaGetLastError());
+    *tmacs_out = best;
+    return CFLX_OK;
 }
 
 // digit planes of rows [0, n) of L^T (LT[k][row], ld) -> A planes

@@ -60,16 +60,6 @@ __device__ __forceinline__ uint4 ld_ll2(const uint2* p) {  // two consecutive LL
     return v;
 }
 
-// ---- thread-block-cluster helpers (DSMEM exchange for small panels) ----
-__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ void st_dsmem_b64(const void* local_smem_ptr, unsigned peer_cta, unsigned long long v) {
-    unsigned remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(peer_cta));
-    asm volatile("st.shared::cluster.b64 [%0], %1;" ::"r"(remote), "l"(v) : "memory");
-}
-constexpr int CS_MAX = 16;  // non-portable cluster size limit on B200
-
 struct Cand {
     unsigned long long key;  // bits of |a| (monotone for non-negative doubles)
     int pos;                 // LAPACK position (tie-break: smaller wins); INT_MAX = no candidate
@@ -117,22 +107,19 @@ __device__ __forceinline__ Cand block_argmax(Cand c, unsigned long long* red_key
     return best;
 }
 
-template <int NB, int RPT_MAX, bool CLUSTER>
+template <int NB, int RPT_MAX>
 __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Ab = reinterpret_cast<double*>(smem_raw);  // [NB][Rpad] inner block, column-major per CTA
     double* U12 = Ab + (size_t)NB * p.Rpad;            // [NB][v]
     double* LU11 = U12 + (size_t)NB * p.v;             // [NB][NB+1] LU rows of this block's pivots
-    double* prow = LU11 + NB * (NB + 1);               // [NB]
-    unsigned long long* red_key = reinterpret_cast<unsigned long long*>(prow + NB);
+    double* prow = LU11 + NB * (NB + 1);               // [2][NB] winner rows, double-buffered by column parity
+    unsigned long long* red_key = reinterpret_cast<unsigned long long*>(prow + 2 * NB);
     int* red_pos = reinterpret_cast<int*>(red_key + 2 * PT_WARPS);
     int* red_row = red_pos + 2 * PT_WARPS;
     int* pivrow_blk = red_row + 2 * PT_WARPS;  // [NB]
-    // cluster mode: candidate slots written by every CTA of the cluster straight into my shared memory
-    // cslot[parity][cta][0] = key, [1] = pos | row << 32, [2..2+NB) = the candidate's inner-block row
-    int* win_sh = pivrow_blk + NB;  // [2] winner {pos, row} broadcast by warp 0 (grid mode)
-    unsigned long long* cslot = reinterpret_cast<unsigned long long*>(pivrow_blk + NB + 2 + (NB & 1));
-    unsigned char* s_act = reinterpret_cast<unsigned char*>(cslot + 2 * CS_MAX * (NB + 2));  // [Rpad] row still active?
+    int* win_sh = pivrow_blk + NB;  // [2][2] winner {pos, row} broadcast by the gathering warp, by column parity
+    unsigned char* s_act = reinterpret_cast<unsigned char*>(win_sh + 4);  // [Rpad] row still active?
     int rb = 0;
 
     const int t = threadIdx.x;
@@ -173,71 +160,58 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
         // (each thread touches only its own rows of Ab until a winner row is published after a block sync)
         TICK(5)
 
-        // ---- phase B: nsb pivot steps ----
-        for (int j = 0; j < nsb; ++j) {
-            const int jg = jb + j;
+        // ---- phase B: nsb pivot steps, software-pipelined across columns ----
+        // The candidate of column j+1 is found and PUBLISHED as soon as the multipliers of column j are known (only
+        // column j+1 of the inner block is updated first); the remaining columns of elimination j are applied while
+        // the exchange is in flight, so its latency hides the rank-1 update instead of adding to it.
+        auto local_candidate = [&](int col) -> Cand {
             Cand c{0ull, INT_MAX, -1};
 #pragma unroll
             for (int q = 0; q < RPT_MAX; ++q) {
                 const int lr = t + q * PT_THREADS;
                 if (active[q]) {
-                    Cand o{(unsigned long long)__double_as_longlong(fabs(Ab[j * Rpad + lr])), pos[q], row_base + lr};
+                    Cand o{(unsigned long long)__double_as_longlong(fabs(Ab[col * Rpad + lr])), pos[q], row_base + lr};
                     if (better(o, c)) c = o;
                 }
             }
-            const Cand mine = block_argmax(c, red_key, red_pos, red_row, rb);
-            TICK(0)
+            return block_argmax(c, red_key, red_pos, red_row, rb);
+        };
+        // publish my CTA's candidate for global column jg and its inner-block row (LL words, fire and forget).  jprev >= 0:
+        // elimination jprev has been applied to column jprev+1 only; the other trailing columns of the candidate's row
+        // are eliminated on the fly with the SAME fma the owner thread will apply later (pw = winner row of jprev).
+        auto publish = [&](const Cand& mine, int jg, int jprev, const double* pw) {
+            const unsigned epoch = (unsigned)(p.epoch_base + jg + 1);
             const int par = jg & 1;
-            Cand win;
-            const double* pr;  // the winner's inner-block row
-            if constexpr (CLUSTER) {
-                // every CTA deposits {key, pos|row, row values} into the slot [par][cta] of EVERY CTA of the cluster
-                // (DSMEM stores), one cluster barrier, then each warp picks the winner from its own shared memory
-                unsigned long long* myslot = cslot + (size_t)(par * CS_MAX + cta) * (NB + 2);
-                const int words = nbc + 2;
-                const int lrw = mine.row >= 0 ? mine.row - row_base : 0;
-                for (int e = t; e < p.G * words; e += PT_THREADS) {
-                    const int peer = e / words, w = e % words;
-                    unsigned long long val;
-                    if (w == 0) val = mine.key;
-                    else if (w == 1) val = (unsigned long long)(unsigned)mine.pos | ((unsigned long long)(unsigned)mine.row << 32);
-                    else val = (unsigned long long)__double_as_longlong(Ab[(w - 2) * Rpad + lrw]);
-                    st_dsmem_b64(myslot + w, (unsigned)peer, val);
-                }
-                cluster_arrive_release();
-                cluster_wait_acquire();
-                TICK(1)
-                Cand gc{0ull, INT_MAX, -1};
-                const int lane = t & 31;
-                if (lane < p.G) {
-                    const unsigned long long* sl = cslot + (size_t)(par * CS_MAX + lane) * (NB + 2);
-                    const unsigned long long pr2 = sl[1];
-                    gc = Cand{sl[0], (int)(unsigned)pr2, (int)(unsigned)(pr2 >> 32)};
-                }
-                win = warp_argmax(gc);
-                TICK(2)
-                const int wcta = win.row / p.R;
-                pr = reinterpret_cast<const double*>(cslot + (size_t)(par * CS_MAX + wcta) * (NB + 2) + 2);
-                if (t < nbc) LU11[j * (NB + 1) + t] = pr[t];
-            } else {
-                // publish my CTA's candidate and its inner-block row (LL words, fire and forget)
+            uint2* myhdr = p.slot_hdr + (size_t)(par * MAXG + cta) * 4;
+            if (t < 4) {
+                const unsigned w = t == 0 ? (unsigned)mine.key : t == 1 ? (unsigned)(mine.key >> 32)
+                                 : t == 2 ? (unsigned)mine.pos : (unsigned)mine.row;
+                st_ll(myhdr + t, w, epoch);
+            }
+            if (mine.row >= 0 && t < nbc) {
+                const int lrw = mine.row - row_base;
+                double x = Ab[t * Rpad + lrw];
+                if (jprev >= 0 && t > jprev + 1) x = fma(-Ab[jprev * Rpad + lrw], pw[t], x);
+                const unsigned long long xb = (unsigned long long)__double_as_longlong(x);
+                uint2* myrow = p.slot_rows + (size_t)(par * MAXG + cta) * 64 + 2 * t;
+                st_ll(myrow, (unsigned)xb, epoch);
+                st_ll(myrow + 1, (unsigned)(xb >> 32), epoch);
+            }
+        };
+        {
+            const Cand mine0 = local_candidate(0);
+            TICK(0)
+            if (t < 32) __threadfence();  // publisher-side half of the per-block release of my phase-C stores (cumulative)
+            publish(mine0, jb, -1, nullptr);
+        }
+        for (int j = 0; j < nsb; ++j) {
+            const int jg = jb + j;
+            const int par = jg & 1;
+            double* pr = prow + par * NB;  // the winner's inner-block row
+            {
+                // gather every CTA's candidate for column jg, pick the winner, fetch its inner-block row.  G <= 32: warp 0
+                // alone (one slot per lane, warp-level argmax, no block barrier); larger grids poll with all warps.
                 const unsigned epoch = (unsigned)(p.epoch_base + jg + 1);
-                uint2* myhdr = p.slot_hdr + (size_t)(par * MAXG + cta) * 4;
-                if (j == 0 && t < 32) __threadfence();  // publisher-side half of the per-block release (cumulative)
-                if (t < 4) {
-                    const unsigned w = t == 0 ? (unsigned)mine.key : t == 1 ? (unsigned)(mine.key >> 32)
-                                     : t == 2 ? (unsigned)mine.pos : (unsigned)mine.row;
-                    st_ll(myhdr + t, w, epoch);
-                }
-                if (mine.row >= 0 && t < nbc) {
-                    const unsigned long long x = (unsigned long long)__double_as_longlong(Ab[t * Rpad + (mine.row - row_base)]);
-                    uint2* myrow = p.slot_rows + (size_t)(par * MAXG + cta) * 64 + 2 * t;
-                    st_ll(myrow, (unsigned)x, epoch);
-                    st_ll(myrow + 1, (unsigned)(x >> 32), epoch);
-                }
-                // warp 0 alone gathers every CTA's candidate (G <= 32: one slot per lane), picks the winner with a
-                // warp-level argmax (no block barrier) and fetches the winner's inner-block row; the other warps wait
-                // at the single barrier below.  Larger grids poll with all warps and reduce block-wide.
                 if (p.G > 32) {
                     Cand gc{0ull, INT_MAX, -1};
                     for (int g = t; g < p.G; g += PT_THREADS) {
@@ -261,12 +235,12 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                             a = ld_ll2(wr);
                         } while (a.y != epoch || a.w != epoch);
                         const double x = __longlong_as_double((long long)(((unsigned long long)a.z << 32) | a.x));
-                        prow[t] = x;
+                        pr[t] = x;
                         LU11[j * (NB + 1) + t] = x;
                     }
                     if (t == 0) {
-                        win_sh[0] = w.pos;
-                        win_sh[1] = w.row;
+                        win_sh[2 * par] = w.pos;
+                        win_sh[2 * par + 1] = w.row;
                     }
                 } else if (t < 32) {
                     Cand gc{0ull, INT_MAX, -1};
@@ -291,22 +265,20 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                             a = ld_ll2(wr);
                         } while (a.y != epoch || a.w != epoch);
                         const double x = __longlong_as_double((long long)(((unsigned long long)a.z << 32) | a.x));
-                        prow[t] = x;
+                        pr[t] = x;
                         LU11[j * (NB + 1) + t] = x;
                     }
                     if (t == 0) {
-                        win_sh[0] = w.pos;
-                        win_sh[1] = w.row;
+                        win_sh[2 * par] = w.pos;
+                        win_sh[2 * par + 1] = w.row;
                     }
                 }
-                pr = prow;
             }
-            if constexpr (!CLUSTER) {
-                __syncthreads();
-                win.key = 0;
-                win.pos = win_sh[0];
-                win.row = win_sh[1];
-            }
+            __syncthreads();  // winner + its row are in shared memory; every thread has finished elimination j-1
+            Cand win;
+            win.key = 0;
+            win.pos = win_sh[2 * par];
+            win.row = win_sh[2 * par + 1];
             if (t == 0) {
                 pivrow_blk[j] = win.row;
                 if (cta == 0) p.perm_out[jg] = win.row;
@@ -314,6 +286,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
             TICK(3)
             const double pivot = pr[j];
             const double rinv = pivot != 0.0 ? 1.0 / pivot : 0.0;
+            const bool have_next = (j + 1 < nbc);
+            const double pnext = have_next ? pr[j + 1] : 0.0;
             double lq[RPT_MAX];
 #pragma unroll
             for (int q = 0; q < RPT_MAX; ++q) {
@@ -331,11 +305,18 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                     lq[q] = Ab[j * Rpad + lr] * rinv;
                     Ab[j * Rpad + lr] = lq[q];
                 }
+                if (have_next) Ab[(j + 1) * Rpad + lr] = fma(-lq[q], pnext, Ab[(j + 1) * Rpad + lr]);  // next column first
+            }
+            if (j + 1 < nsb) {
+                const Cand mine = local_candidate(j + 1);  // (its block barrier also orders the multiplier stores above)
+                TICK(0)
+                publish(mine, jg + 1, j, pr);
+                __syncthreads();  // the candidate row's pre-update values have been read before its owner updates them
             }
             {
                 double* __restrict__ ab = Ab;
 #pragma unroll 4
-                for (int c2 = j + 1; c2 < nbc; ++c2) {
+                for (int c2 = j + 2; c2 < nbc; ++c2) {
                     const double pc = pr[c2];
 #pragma unroll
                     for (int q = 0; q < RPT_MAX; ++q) {
@@ -345,7 +326,6 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                 }
             }
             TICK(4)
-            // next step's block_argmax syncs before prow / LU11 are overwritten
         }
 
         // ---- write the inner block back (L multipliers; pivot rows keep their LU row) ----
@@ -476,51 +456,27 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
 
 template <int NB>
 size_t panel_smem_bytes(int Rpad, int v) {
-    return ((size_t)NB * Rpad + (size_t)NB * v + NB * (NB + 1) + NB) * sizeof(double) +
-           2 * PT_WARPS * (sizeof(unsigned long long) + 2 * sizeof(int)) + (NB + 4) * sizeof(int) +
-           2 * CS_MAX * (NB + 2) * sizeof(unsigned long long) + (size_t)Rpad + 64;
+    return ((size_t)NB * Rpad + (size_t)NB * v + NB * (NB + 1) + 2 * NB) * sizeof(double) +
+           2 * PT_WARPS * (sizeof(unsigned long long) + 2 * sizeof(int)) + (NB + 4) * sizeof(int) + (size_t)Rpad + 64;
 }
 
 template <int NB, int RPT>
-int launch_nb_rpt(PanelArgs& a, bool cluster, cudaStream_t stream) {
+int launch_nb_rpt(PanelArgs& a, cudaStream_t stream) {
     const size_t smem = panel_smem_bytes<NB>(a.Rpad, a.v);
     void* params[] = {&a};
-    if (cluster) {
-        // one thread-block cluster of G (<= 16) CTAs: candidates are exchanged through distributed shared memory
-        static PerDeviceMax cfg;
-        if (cfg.raise(smem)) {
-            CFLX_CUDA(cudaFuncSetAttribute(panel_getrf_kernel<NB, RPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CFLX_CUDA(cudaFuncSetAttribute(panel_getrf_kernel<NB, RPT, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        }
-        cudaLaunchConfig_t cfgl{};
-        cfgl.gridDim = dim3(a.G);
-        cfgl.blockDim = dim3(PT_THREADS);
-        cfgl.dynamicSmemBytes = smem;
-        cfgl.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = a.G;
-        at[0].val.clusterDim.y = 1;
-        at[0].val.clusterDim.z = 1;
-        cfgl.attrs = at;
-        cfgl.numAttrs = 1;
-        if (cudaLaunchKernelExC(&cfgl, (const void*)panel_getrf_kernel<NB, RPT, true>, params) == cudaSuccess) return CFLX_OK;
-        cudaGetLastError();  // cluster shape not launchable here: fall through to the grid-wide (LL exchange) variant
-    }
     static PerDeviceMax cfg;
     if (cfg.raise(smem))
-        CFLX_CUDA(cudaFuncSetAttribute(panel_getrf_kernel<NB, RPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CFLX_CUDA(cudaLaunchCooperativeKernel((void*)panel_getrf_kernel<NB, RPT, false>, dim3(a.G), dim3(PT_THREADS), params, smem,
-                                          stream));
+        CFLX_CUDA(cudaFuncSetAttribute(panel_getrf_kernel<NB, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CFLX_CUDA(cudaLaunchCooperativeKernel((void*)panel_getrf_kernel<NB, RPT>, dim3(a.G), dim3(PT_THREADS), params, smem, stream));
     return CFLX_OK;
 }
 template <int NB>
-int launch_nb(PanelArgs& a, bool cluster, cudaStream_t stream) {
+int launch_nb(PanelArgs& a, cudaStream_t stream) {
     const int rpt = (a.R + PT_THREADS - 1) / PT_THREADS;
-    if (rpt <= 1) return launch_nb_rpt<NB, 1>(a, cluster, stream);
-    if (rpt <= 2) return launch_nb_rpt<NB, 2>(a, cluster, stream);
-    if (rpt <= 4) return launch_nb_rpt<NB, 4>(a, cluster, stream);
-    return launch_nb_rpt<NB, 8>(a, cluster, stream);
+    if (rpt <= 1) return launch_nb_rpt<NB, 1>(a, stream);
+    if (rpt <= 2) return launch_nb_rpt<NB, 2>(a, stream);
+    if (rpt <= 4) return launch_nb_rpt<NB, 4>(a, stream);
+    return launch_nb_rpt<NB, 8>(a, stream);
 }
 }  // namespace
 
@@ -557,15 +513,6 @@ int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, 
     a.n = n;
     a.v = v;
     a.nsteps = n < v ? n : v;
-    // Small panels (late steps, tournament stacks) are latency-bound by the per-column exchange: run them as ONE
-    // cluster of <= 16 CTAs that exchanges candidates through distributed shared memory.  CFLX_CLUSTER_ROWS sets the
-    // largest n handled that way (0 disables).
-    static int cluster_rows = -1;
-    if (cluster_rows < 0) {
-        const char* e = getenv("CFLX_CLUSTER_ROWS");
-        cluster_rows = e ? atoi(e) : 0;  // opt-in until validated on hardware
-    }
-    const bool cluster = (n <= cluster_rows) && (n <= CS_MAX * RPT_LIMIT * PT_THREADS);
     // as many CTAs as the cap allows down to 32 rows per CTA: small panels (late steps, tournament stacks) are spread
     // over up to 32 SMs and the threads that share a row split the trailing columns in phase C
     int G = (n + 31) / 32;
@@ -577,7 +524,6 @@ int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, 
         const int need = (n + RPT_LIMIT * PT_THREADS - 1) / (RPT_LIMIT * PT_THREADS);
         if (G < need) G = need < ws->max_ctas ? need : ws->max_ctas;
     }
-    if (cluster && G > CS_MAX) G = CS_MAX;
     int R = (n + G - 1) / G;
     R = (int)round_up(R > 0 ? R : 1, 32);
     G = n > 0 ? (n + R - 1) / R : 1;
@@ -608,10 +554,10 @@ int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, 
     }
     if (nb_used) *nb_used = nb;
     switch (nb) {
-        case 32: return launch_nb<32>(a, cluster, stream);
-        case 16: return launch_nb<16>(a, cluster, stream);
-        case 8: return launch_nb<8>(a, cluster, stream);
-        default: return launch_nb<4>(a, cluster, stream);
+        case 32: return launch_nb<32>(a, stream);
+        case 16: return launch_nb<16>(a, stream);
+        case 8: return launch_nb<8>(a, stream);
+        default: return launch_nb<4>(a, stream);
     }
 }
 

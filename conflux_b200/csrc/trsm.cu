@@ -3,8 +3,8 @@
 // Replaces, relative to /root/reference/src/conflux/lu/conflux_opt.hpp:
 //   :1347-1358  cblas_dtrsm(Right, Upper, NoTrans, NonUnit)  A10 <- A10 * U00^-1     -> trsm_right_upper_T
 //   :1539-1550  cblas_dtrsm(Left,  Lower, NoTrans, Unit)     A01 <- L00^-1 * A01     -> trsm_left_lower_unit
-// A00 = L00\U00 is v x v (<= 2 MB).  Its nb x nb diagonal blocks are inverted once per step by a small kernel
-// (one CTA per block, substitution in shared memory); the solve is then a right-looking sweep of GEMMs
+// A00 = L00\U00 is v x v (<= 2 MB).  Its nb x nb diagonal blocks (nb = 128 when v allows, like MAGMA's trsm) are inverted
+// once per step by a small kernel (substitution in shared memory, one warp per column); the solve is then a right-looking sweep of GEMMs
 // (multiply by the inverse block, rank-nb update of the remaining block rows) that all run on gemm.cu's DMMA
 // kernel with the panels kept K-major (transposed L panel, row-major U panel).
 #include "common.cuh"
@@ -12,62 +12,88 @@
 
 namespace cflx {
 namespace {
-// grid = (nblk, 2): y == 0 -> Uinv[j] = inv(U_jj) row-major; y == 1 -> LinvT[j] = inv(L_jj)^T row-major.
-// One WARP per column of the inverse: the column lives in registers spread over the lanes (lane l holds entries l and
-// l + 32), every substitution step is a two-term partial dot product per lane + a warp reduction, so a 64 x 64 block
-// takes 64 steps of ~100 cycles per column instead of a 2000-FMA serial chain per thread.
+// grid = (nblk, 2, CS): y == 0 -> Uinv[j] = inv(U_jj) row-major; y == 1 -> LinvT[j] = inv(L_jj)^T row-major; the columns of
+// a block are split over CS = gridDim.z CTAs (each stages the whole block in shared memory).
+// One WARP per column of the inverse: the column lives in registers spread over the lanes (lane l holds entries l, l + 32,
+// ...), every substitution step is a short partial dot product per lane + a warp reduction, so an NB x NB block takes NB
+// steps of ~100 cycles per column instead of an NB^2 / 2 serial FMA chain per thread.
 template <int NB>
 __global__ void __launch_bounds__(1024) diag_inverse_kernel(const double* __restrict__ A00, int v, double* __restrict__ Uinv,
                                                             double* __restrict__ LinvT) {
-    static_assert(NB <= 64, "two entries per lane");
-    __shared__ double S[NB][NB + 1];
+    constexpr int EPL = (NB + 31) / 32;  // entries per lane
+    extern __shared__ double S[];        // [NB][NB + 1]
+    constexpr int LD = NB + 1;
     const int j = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const double* blk = A00 + (size_t)(j * NB) * v + j * NB;
-    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) S[e / NB][e % NB] = blk[(size_t)(e / NB) * v + e % NB];
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) S[(e / NB) * LD + e % NB] = blk[(size_t)(e / NB) * v + e % NB];
     __syncthreads();
     double* out = (blockIdx.y == 0 ? Uinv : LinvT) + (size_t)j * NB * NB;
-    const int t0 = lane, t1 = lane + 32;
-    for (int c = warp; c < NB; c += nwarps) {
-        double x0 = 0.0, x1 = 0.0;  // entries t0 and t1 of column c
+    const int cols_per = (NB + gridDim.z - 1) / gridDim.z;
+    const int c_lo = blockIdx.z * cols_per, c_hi = min(NB, c_lo + cols_per);
+    for (int c = c_lo + warp; c < c_hi; c += nwarps) {
+        double x[EPL];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) x[e] = 0.0;
         if (blockIdx.y == 0) {  // U X = I: x[c] = 1/U[c][c]; x[r] = -(sum_{t=r+1..c} U[r][t] x[t]) / U[r][r], r < c
-            const double xc = 1.0 / S[c][c];
-            if (t0 == c) x0 = xc;
-            if (t1 == c) x1 = xc;
+            const double xc = 1.0 / S[c * LD + c];
+#pragma unroll
+            for (int e = 0; e < EPL; ++e)
+                if (lane + 32 * e == c) x[e] = xc;
             for (int r = c - 1; r >= 0; --r) {
                 double s = 0.0;
-                if (t0 > r && t0 <= c) s = S[r][t0] * x0;
-                if (t1 > r && t1 <= c && t1 < NB) s = fma(S[r][t1], x1, s);
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) {
+                    const int t = lane + 32 * e;
+                    if (t > r && t <= c) s = fma(S[r * LD + t], x[e], s);
+                }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                const double xr = -s / S[r][r];
-                if (t0 == r) x0 = xr;
-                if (t1 == r) x1 = xr;
+                const double xr = -s / S[r * LD + r];
+#pragma unroll
+                for (int e = 0; e < EPL; ++e)
+                    if (lane + 32 * e == r) x[e] = xr;
             }
-            if (t0 < NB) out[(size_t)t0 * NB + c] = x0;  // Uinv[r][c]
-            if (t1 < NB) out[(size_t)t1 * NB + c] = x1;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) {
+                const int t = lane + 32 * e;
+                if (t < NB) out[(size_t)t * NB + c] = x[e];  // Uinv[r][c]
+            }
         } else {  // L Y = I (unit diagonal): y[c] = 1; y[r] = -sum_{t=c..r-1} L[r][t] y[t], r > c
-            if (t0 == c) x0 = 1.0;
-            if (t1 == c) x1 = 1.0;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e)
+                if (lane + 32 * e == c) x[e] = 1.0;
             for (int r = c + 1; r < NB; ++r) {
                 double s = 0.0;
-                if (t0 >= c && t0 < r) s = S[r][t0] * x0;
-                if (t1 >= c && t1 < r) s = fma(S[r][t1], x1, s);
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) {
+                    const int t = lane + 32 * e;
+                    if (t >= c && t < r) s = fma(S[r * LD + t], x[e], s);
+                }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (t0 == r) x0 = -s;
-                if (t1 == r) x1 = -s;
+#pragma unroll
+                for (int e = 0; e < EPL; ++e)
+                    if (lane + 32 * e == r) x[e] = -s;
             }
-            if (t0 < NB) out[(size_t)c * NB + t0] = x0;  // LinvT[c][r] = Linv[r][c]
-            if (t1 < NB) out[(size_t)c * NB + t1] = x1;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) {
+                const int t = lane + 32 * e;
+                if (t < NB) out[(size_t)c * NB + t] = x[e];  // LinvT[c][r] = Linv[r][c]
+            }
         }
     }
 }
 
 template <int NB>
 int launch_diag_nb(const double* A00, int v, double* Uinv, double* LinvT, cudaStream_t stream) {
-    const int warps = NB < 32 ? NB : 32;  // one warp per column (two columns per warp at NB = 64)
-    diag_inverse_kernel<NB><<<dim3(v / NB, 2), 32 * warps, 0, stream>>>(A00, v, Uinv, LinvT);
+    constexpr size_t smem = (size_t)NB * (NB + 1) * sizeof(double);
+    constexpr int CS = NB > 64 ? NB / 32 : 1;   // 128-wide blocks: 4 CTAs x 32 columns, one column per warp
+    const int warps = NB < 32 ? NB : 32;
+    static PerDeviceMax cfg;
+    if (cfg.raise(smem))
+        CFLX_CUDA(cudaFuncSetAttribute(diag_inverse_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    diag_inverse_kernel<NB><<<dim3(v / NB, 2, CS), 32 * warps, smem, stream>>>(A00, v, Uinv, LinvT);
     CFLX_CUDA(cudaGetLastError());
     return CFLX_OK;
 }
@@ -75,6 +101,7 @@ int launch_diag_nb(const double* A00, int v, double* Uinv, double* LinvT, cudaSt
 
 int launch_diag_inverses(const double* A00, int v, int nb, double* Uinv, double* LinvT, cudaStream_t stream) {
     switch (nb) {
+        case 128: return launch_diag_nb<128>(A00, v, Uinv, LinvT, stream);
         case 64: return launch_diag_nb<64>(A00, v, Uinv, LinvT, stream);
         case 32: return launch_diag_nb<32>(A00, v, Uinv, LinvT, stream);
         case 16: return launch_diag_nb<16>(A00, v, Uinv, LinvT, stream);

@@ -123,6 +123,9 @@ int cflx_dbg_trsm(int n, int v, const double* A00, const double* B, double* X_ou
 int cflx_dbg_ozaki_gemm(int M, int N, int K, const double* AT, const double* B, const double* C, double* D,
                         signed char* planesA_out, signed char* planesB_out, int* ea_out, int* eb_out, int reps,
                         double* ms_out, double* split_ms_out);
+/* raw tensor-pipe rate of back-to-back tcgen05.mma (128 x n x 32 bytes of K, operands resident in shared memory, one
+ * CTA per SM): which = 0 kind::i8, 1 kind::f16 on bf16.  tmacs_out = tera-MACs/s (x2 = TOP/s). */
+int cflx_dbg_umma_peak(int which, int n, double* tmacs_out);
 /* plan_moves + push_phase1..3 + gri bookkeeping on one rank: the npiv pivot rows (local indices >= fnpr, tournament
  * order) are pushed to rows [fnpr, fnpr+npiv) exactly like push_pivots_up (conflux_opt.hpp:176-218, tests/unit/
  * test_utils.cpp:8-84).  n_cols even.  gri_out[n_rows] = new row -> old row, a01_out[npiv*n_cols] = extracted rows. */
