@@ -209,8 +209,108 @@ def load_traffic(M, N, K):
     return None, None
 
 
+CHOL_WORKLOAD = (32768, 512)     # BASELINE.json configs[4]: cholesky_miniapp --dim=32768 --tile=512 (8 x B200)
+
+
+def run_cholesky(args, rank, world, local_rank):
+    """`--algo cholesky`: the CONFCHOX path (BASELINE config C5) at --gpus N, strong scaling (same matrix at every N), the
+    reference's automatic grid (Cholesky.cpp:75-111: 8 -> 4x2x1).  Same JSON contract as the LU line."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import conflux_b200 as cb
+    from conflux_b200 import _lib
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    N, v = CHOL_WORKLOAD
+    if args.N:
+        N = args.N
+    if args.v:
+        v = args.v
+    comm = cb.Comm.from_torch_distributed(device=local_rank) if world > 1 else cb.Comm(1, 0, None, local_rank)
+    ch = cb.cholesky.initialize(N, v, (0, 0, 0), comm)
+    host = cb.pinned_empty((ch.Ml, ch.Nl))
+    host[...] = ch.data
+    ch.data = host
+    flops = float(ch.N) ** 3 / 3.0
+
+    def barrier():
+        comm.barrier()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peak = cb.dbg.fp64_peak_ex(0)[0] if rank == 0 else None
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ch.parallelCholesky(upload=True)
+    for _ in range(max(args.warmup, 3) - 1):
+        ch.parallelCholesky(upload=False)
+    cnt = ctypes.c_int64()
+    _lib.lib().cflx_chol_launch_count(ch._h, ctypes.byref(cnt), 1)
+    barrier()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        dev_ms += ch.parallelCholesky(upload=False)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    _lib.lib().cflx_chol_launch_count(ch._h, ctypes.byref(cnt), 1)
+    dev_ms = max_over_ranks(dev_ms)
+    ms_step = dev_ms / args.steps
+    value = flops / (ms_step * 1e-3) / 1e9
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ch.parallelCholesky(upload=True)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    resid_abs, resid = ch.validate()
+    if rank == 0:
+        grid = (ch.PX, ch.PY, ch.PZ)
+        line = {"metric": "Cholesky GFLOP/s (FP64, (1/3)N^3)", "value": value, "unit": "GFLOP/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"cholesky N={ch.N} v={ch.v} grid {grid[0]}x{grid[1]}x{grid[2]}",
+                           "generator": "CholeskyIO::generateInputMatrixDistributed (tile = lower(R^T R), srand(1), diagonal 2*Kappa*max row sum)",
+                           "l2": "inputs larger than L2 (local matrix %.1f GiB)" % (ch.Ml * ch.Nl * 8 / 2 ** 30)},
+                "timing": "CUDA events on the launching stream around each factorisation loop, max over ranks",
+                "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": int(ch.Ml * ch.Nl * 8), "d2h_bytes_per_step": 0},
+                "gpu_launches": int(cnt.value), "clocks": clocks,
+                "roofline": {"bound": "tensor", "kernel": "whole path (gemm_tn_kernel, DMMA.8x8x4, does the rank-v updates)",
+                             "achieved": value / 1e3 / args.gpus, "peak": peak, "unit": "TFLOP/s per GPU",
+                             "frac": value / 1e3 / args.gpus / peak if peak else None, "traffic": None},
+                "parity": {"residual_A_minus_LLt_rel_frobenius": resid, "residual_A_minus_LLt_abs_frobenius": resid_abs,
+                           "residual_tolerance": 1e-12, "residual_how": "cflx_chol_validate: update sweep replayed with the stored factor on the grid"}}
+        if args.gpus == 1 and not args.no_cpu_baseline:
+            import scipy.linalg
+            n_s = 8192
+            A = np.random.default_rng(0).standard_normal((n_s, 64))
+            S = A @ A.T + n_s * np.eye(n_s)
+            t1 = time.perf_counter()
+            scipy.linalg.cholesky(S, lower=True, overwrite_a=True, check_finite=False)
+            dt = time.perf_counter() - t1
+            line["cpu_baseline"] = {"value": n_s ** 3 / 3.0 / dt / 1e9, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"LAPACK dpotrf (scipy/OpenBLAS) N={n_s}, one call -- the reference's own checker "
+                                              "(cholesky_helper.cpp:183-217); its MPI driver needs >= 4 ranks and MPI, absent here"}
+        print(json.dumps(line))
+    ch.finalize()
+    comm.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--algo", default="lu", choices=["lu", "cholesky"], help="cholesky = BASELINE config C5 (not the driver's default)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
@@ -225,6 +325,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank)
+        return
+    if args.algo == "cholesky":
+        if world != args.gpus:
+            raise SystemExit(f"--gpus {args.gpus} needs WORLD_SIZE == {args.gpus} (launch N>1 with torchrun)")
+        run_cholesky(args, rank, world, local_rank)
         return
     if args.gpus not in WORKLOADS or world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} needs WORLD_SIZE == {args.gpus} in {sorted(WORKLOADS)} (launch N>1 with torchrun)")

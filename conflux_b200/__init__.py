@@ -15,7 +15,7 @@ import numpy as np
 
 from ._lib import ConfluxError, LIB_PATH, SYMBOLS, check, lib
 
-__all__ = ["pinned_empty", "pinned_free", "Comm", "lu_params", "LU_rep", "residual", "validate", "timeline", "auto_grid", "lu_dims", "init_matrix_host", "ConfluxError", "dbg"]
+__all__ = ["pinned_empty", "pinned_free", "Comm", "lu_params", "LU_rep", "residual", "validate", "timeline", "auto_grid", "lu_dims", "init_matrix_host", "ConfluxError", "dbg", "cholesky", "chol_dims", "chol_auto_grid"]
 
 
 def auto_grid(M, N, P):
@@ -192,6 +192,74 @@ def validate(gv):
 def residual(gv):
     """||PA - LU||_F / ||A||_F of the last LU_rep, computed on the GPU grid (collective)."""
     return validate(gv)[1]
+
+
+class cholesky:
+    """Mirror of the reference's CONFCHOX driver interface (src/conflux/cholesky/Cholesky.h:20-22):
+        initialize(N, v, grid, comm) -> object;  obj.parallelCholesky() -> ms;  obj.finalize().
+    grid = (0, 0, 0) and v = 0 select the reference's automatic choices (Cholesky.cpp:75-134).  `data` is this rank's share
+    of the input (Ml x Nl, conflux tile layout), filled by the reference's generator (CholeskyIO.cpp:100-172)."""
+
+    def __init__(self, N, v, grid, comm):
+        self.comm = comm
+        self._h = ctypes.c_void_p()
+        g = tuple(int(x) for x in grid)
+        check(lib().cflx_chol_create(comm._h, int(N), int(v), g[0], g[1], g[2], ctypes.byref(self._h)), "chol_create")
+        info = (ctypes.c_int * 16)()
+        check(lib().cflx_chol_info(self._h, info), "chol_info")
+        (self.N, self.v, self.Kappa, self.Ml, self.Nl, self.l, self.P, self.PX, self.PY, self.PZ, self.px, self.py, self.pz,
+         self.rank) = list(info)[:14]
+        self.data = np.zeros((self.Ml, self.Nl))
+        self.generateInputMatrixDistributed()
+
+    @classmethod
+    def initialize(cls, N, v, grid, comm):
+        return cls(N, v, grid, comm)
+
+    def generateInputMatrixDistributed(self):
+        check(lib().cflx_chol_init_matrix_host(self.N, self.v, self.PX, self.PY, self.PZ, self.rank, self.data.ctypes.data),
+              "chol_init_matrix_host")
+
+    def parallelCholesky(self, upload=True):
+        if upload:
+            a = np.ascontiguousarray(self.data, dtype=np.float64)
+            check(lib().cflx_chol_set_local(self._h, a.ctypes.data), "chol_set_local")
+        ms = ctypes.c_double()
+        check(lib().cflx_chol_factor(self._h, ctypes.byref(ms)), "chol_factor")
+        return ms.value
+
+    def local_factor(self):
+        L = np.empty((self.Ml, self.Nl))
+        check(lib().cflx_chol_get_local(self._h, L.ctypes.data), "chol_get_local")
+        return L
+
+    def validate(self):
+        a, r = ctypes.c_double(), ctypes.c_double()
+        check(lib().cflx_chol_validate(self._h, ctypes.byref(a), ctypes.byref(r)), "chol_validate")
+        return a.value, r.value
+
+    def finalize(self, clean=True):
+        if self._h:
+            lib().cflx_chol_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.finalize()
+        except Exception:
+            pass
+
+
+def chol_dims(N, v, Px, Py, Pz):
+    o = (ctypes.c_int * 6)()
+    check(lib().cflx_chol_dims(int(N), int(v), int(Px), int(Py), int(Pz), o), "chol_dims")
+    return dict(N=o[0], Kappa=o[1], Ml=o[2], Nl=o[3], l=o[4], P=o[5])
+
+
+def chol_auto_grid(P, N):
+    g = (ctypes.c_int * 3)()
+    check(lib().cflx_chol_auto_grid(int(P), int(N), g), "chol_auto_grid")
+    return tuple(g)
 
 
 class dbg:

@@ -108,6 +108,33 @@ int cflx_lu_set_kernel_timing(cflx_lu*, int enabled);
 int cflx_lu_trailing_stats(cflx_lu*, double* ms_out, double* flops_out);
 void cflx_lu_destroy(cflx_lu*);
 
+/* ---- CONFCHOX: Cholesky factorisation A = L L^T (lower) on the same process grid (BASELINE config C5) -----------------
+ * Reference interfaces replaced (src/conflux/cholesky):
+ *   initialize(argc, argv, N, v, grid)  Cholesky.cpp:60-160 (grid / tile choice :75-134)  -> cflx_chol_auto_grid/_tile, cflx_chol_create
+ *   CholeskyIO::generateInputMatrixDistributed  CholeskyIO.cpp:100-172                   -> cflx_chol_init_matrix_host
+ *   parallelCholesky()                  Cholesky.cpp:760-921                              -> cflx_chol_factor
+ *   finalize(clean)                     Cholesky.cpp:160-175                              -> cflx_chol_destroy
+ * Local data: row-major Ml x Nl, tile (gi, gj) of the v x v tiling on rank (gi % Px, gj % Py) at local tile (gi / Px,
+ * gj / Py); ranks are numbered (pi * Py + pj) * Pz + pk like the LU path; only the lower triangle is referenced. */
+typedef struct cflx_chol cflx_chol;
+int cflx_chol_auto_grid(int P, int N, int* grid3_out);
+int cflx_chol_auto_tile(int N, int P, int Pz);
+/* dims_out[6] = {N padded to a multiple of v, Kappa (tiles per dimension), Ml, Nl, v / Pz, P} */
+int cflx_chol_dims(int N, int v, int Px, int Py, int Pz, int* dims_out);
+int cflx_chol_init_matrix_host(int N, int v, int Px, int Py, int Pz, int rank, double* local_out);
+/* COLLECTIVE.  Px <= 0 / v <= 0 select the reference's automatic choices.  Requires v % 4 == 0, (v / Pz) % 4 == 0, v <= 512. */
+int cflx_chol_create(cflx_comm*, int N, int v, int Px, int Py, int Pz, cflx_chol** out);
+/* info_out[16] = {N, v, Kappa, Ml, Nl, v / Pz, P, Px, Py, Pz, pi, pj, pk, rank, 0, 0} */
+int cflx_chol_info(const cflx_chol*, int* info_out);
+int cflx_chol_set_local(cflx_chol*, const double* host_local);
+/* COLLECTIVE.  ms_out = device time of the factorisation loop (the region the reference's miniapp times). */
+int cflx_chol_factor(cflx_chol*, double* ms_out);
+int cflx_chol_get_local(cflx_chol*, double* L_host);
+/* COLLECTIVE.  ||A - L L^T||_F over the lower triangle, absolute and relative to ||A||_F, computed on the GPU grid. */
+int cflx_chol_validate(cflx_chol*, double* frob_abs_out, double* frob_rel_out);
+int cflx_chol_launch_count(cflx_chol*, int64_t* count_out, int reset);
+void cflx_chol_destroy(cflx_chol*);
+
 /* ---- single-device building blocks exposed for tests and micro-benchmarks (host buffers in, host out) ----- */
 /* D = beta*C + alpha * AT^T * B with AT [K x M], B [K x N], C/D [M x N], all row-major, dense */
 int cflx_dbg_gemm_tn(int M, int N, int K, const double* AT, const double* B, const double* C, double alpha, double beta,

@@ -65,6 +65,36 @@ def test_fixed_input_matrices_are_the_references(golden_dir):
     assert np.array_equal(a, b) and float(a.max()) <= 9.0
 
 
+def test_cholesky_host_rules_match_the_reference():
+    # Cholesky.cpp:75-111 grid choice; :113-134 tile choice; CholeskyProperties (Kappa = N / v tiles, 2-D cyclic A11)
+    assert cb.chol_auto_grid(8, 32768) == (4, 2, 1) and cb.chol_auto_grid(8, 8192) == (2, 2, 2)
+    assert cb.chol_auto_grid(4, 65536) == (2, 2, 1) and cb.chol_auto_grid(16, 4096) == (4, 4, 1)
+    assert cb.chol_auto_grid(2, 4096) == (2, 1, 1) and cb.chol_auto_grid(1, 4096) == (1, 1, 1)
+    assert _lib.lib().cflx_chol_auto_tile(32768, 8, 1) == 512 and _lib.lib().cflx_chol_auto_tile(2048, 4, 1) == 128
+    d = cb.chol_dims(32768, 512, 4, 2, 1)
+    assert (d["Kappa"], d["Ml"], d["Nl"]) == (64, 8192, 16384)
+    d = cb.chol_dims(100, 16, 2, 2, 2)                      # padded to a multiple of v (CholeskyIO.cpp:196-203)
+    assert (d["N"], d["Kappa"], d["Ml"], d["l"]) == (112, 7, 64, 8)
+
+
+def test_cholesky_generator_matches_restatement():
+    """CholeskyIO.cpp:100-172: every tile = lower(R^T R) from rand() after srand(1), strengthened global diagonal."""
+    from oracle import chol_ref
+    N, v, g = 96, 16, (2, 2, 2)
+    A, T, mx = chol_ref.init_matrix(N, v)
+    d = cb.chol_dims(N, v, *g)
+    locs = []
+    for rank in range(8):
+        out = np.zeros((d["Ml"], d["Nl"]))
+        assert _lib.lib().cflx_chol_init_matrix_host(N, v, *g, rank, out.ctypes.data) == 0
+        locs.append(out)
+        if rank % 2:
+            assert not out.any()                            # layers pz != 0 start at zero
+    G = chol_ref.assemble(locs, N, v, *g)
+    assert np.allclose(np.tril(G), A, rtol=1e-14, atol=1e-14)
+    assert np.array_equal(np.diag(G), np.diag(A)) or np.allclose(np.diag(G), np.diag(A), rtol=1e-15)
+
+
 def test_device_entry_points_refuse_without_gpu():
     n = ctypes.c_int(-1)
     assert _lib.lib().cflx_device_count(ctypes.byref(n)) == 0
