@@ -195,7 +195,7 @@ def load_golden_perm(N, v, grid):
     return None
 
 
-def load_traffic(M, N, K):
+def load_traffic(M, N, K, kernel="dmma"):
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the trailing-update kernel, from the committed
     summary of an `ncu --set full` capture (profiles/r02_gemm_traffic.json, written by tools/summarize_ncu.py)."""
     path = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
@@ -204,7 +204,7 @@ def load_traffic(M, N, K):
     except Exception:  # noqa: BLE001
         return None, None
     for e in d.get("launches", []):
-        if (e.get("M"), e.get("N"), e.get("K")) == (M, N, K):
+        if (e.get("kernel", "dmma"), e.get("M"), e.get("N"), e.get("K")) == (kernel, M, N, K):
             return e.get("dram_bytes"), e.get("source")
     return None, None
 
@@ -430,7 +430,7 @@ def main():
         dmma_peak = peak_burst
         g_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         n1 = gv.Ml - gv.v                             # first-step shape of the trailing update (the ncu-captured launch)
-        traffic, traffic_src = load_traffic(n1, gv.Nl - gv.v, gv.nlayr)
+        traffic, traffic_src = load_traffic(n1, gv.Nl - gv.v, gv.nlayr, os.environ.get("CFLX_GEMM", "dmma"))
         grid = (Px, Py, Pz)
         line = {
             "metric": "LU GFLOP/s (FP64, (2/3)N^3)", "value": value, "unit": "GFLOP/s", "n_gpus": args.gpus,

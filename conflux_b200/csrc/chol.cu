@@ -31,10 +31,12 @@ struct cflx_chol {
     int N = 0, v = 0, Kappa = 0, Px = 1, Py = 1, Pz = 1, P = 1, Ml = 0, Nl = 0, nlayr = 0, nb = 0;
     int pi = 0, pj = 0, pk = 0, rank = 0;
     SubComm k_comm, i_comm;
-    double *A0 = nullptr, *A11 = nullptr, *PT = nullptr, *LT = nullptr, *G = nullptr, *Bc = nullptr, *D = nullptr, *A00 = nullptr,
-           *Uinv = nullptr, *LinvT = nullptr, *acc = nullptr;
+    double *A0 = nullptr, *A11 = nullptr, *PT = nullptr, *LT = nullptr, *G = nullptr /* [2] */, *Bc = nullptr /* [2] */, *D = nullptr, *A00 = nullptr,
+           *W = nullptr, *Uinv = nullptr, *LinvT = nullptr, *acc = nullptr;
     int* info = nullptr;
     int64_t ldp = 0, ldb = 0;
+    cudaStream_t side = nullptr;            // panel pipeline of step k+1 (all NCCL traffic lives here) under the update of step k
+    cudaEvent_t ev_col[2] = {nullptr, nullptr}, ev_panel[2] = {nullptr, nullptr};
     bool have_input = false, factored = false;
     int64_t launches = 0;
 };
@@ -154,18 +156,21 @@ __global__ void tile_store_kernel(const double* __restrict__ D, int v, double* _
 }
 // Bc[c][t * v + x] = G_piece(j % Px)[c][(j / Px) * v - row1(j % Px) + x] for the local column tiles t (global j = (lj0 + t) * Py + pj)
 struct GatherArgs {
-    const double* G;       // Px pieces, each [v][ldg]
-    int64_t ldg, piece_stride;
+    const double* G;       // Px pieces, piece p = [v][ld_p] with ld_p = its active rows rounded up to even
+    int64_t piece_stride;
     double* Bc;
     int64_t ldb;
-    int v, Px, Py, pj, lj0, ntiles, k;
+    int v, Px, Py, pj, lj0, ntiles, gfirst, Ml;
 };
 __global__ void gather_cols_kernel(GatherArgs a) {
     const int t = blockIdx.x, c = blockIdx.y;
     const int j = (a.lj0 + t) * a.Py + a.pj;            // global tile index of this local column tile
     const int p = j % a.Px;
-    const int first = (a.k + 1 - p + a.Px - 1) / a.Px;  // first local tile row of piece p that is below tile k
-    const double* src = a.G + (int64_t)p * a.piece_stride + (int64_t)c * a.ldg + (int64_t)(j / a.Px - first) * a.v;
+    const int d = a.gfirst - p;
+    const int first = d <= 0 ? 0 : (d + a.Px - 1) / a.Px;   // first local tile row of piece p that holds a tile >= gfirst
+    const int rows = a.Ml - first * a.v;
+    const int64_t ldg = max(2, (rows + 1) & ~1);
+    const double* src = a.G + (int64_t)p * a.piece_stride + (int64_t)c * ldg + (int64_t)(j / a.Px - first) * a.v;
     double* dst = a.Bc + (int64_t)c * a.ldb + (int64_t)t * a.v;
     for (int x = threadIdx.x; x < a.v; x += blockDim.x) dst[x] = src[x];
 }
@@ -224,8 +229,13 @@ int chol_pick_nb(int v) {
 void free_chol(cflx_chol* ch) {
     if (!ch) return;
     cudaSetDevice(ch->comm->device);
-    for (double* p : {ch->A0, ch->A11, ch->PT, ch->LT, ch->G, ch->Bc, ch->D, ch->A00, ch->Uinv, ch->LinvT, ch->acc}) cudaFree(p);
+    for (double* p : {ch->A0, ch->A11, ch->PT, ch->LT, ch->W, ch->G, ch->Bc, ch->D, ch->A00, ch->Uinv, ch->LinvT, ch->acc}) cudaFree(p);
     cudaFree(ch->info);
+    if (ch->side) cudaStreamDestroy(ch->side);
+    for (int i = 0; i < 2; ++i) {
+        if (ch->ev_col[i]) cudaEventDestroy(ch->ev_col[i]);
+        if (ch->ev_panel[i]) cudaEventDestroy(ch->ev_panel[i]);
+    }
     for (SubComm* sc : {&ch->k_comm, &ch->i_comm})
         if (sc->c) ncclCommDestroy(sc->c);
     delete ch;
@@ -234,48 +244,64 @@ void free_chol(cflx_chol* ch) {
 // Broadcast the Px pieces of the (transposed) panel of column block t to every rank and apply
 //   X[i][j] -= L[i][t] * L[j][t]^T   to the local tiles with global tile row i >= tile column j >= jmin (lower triangle),
 // each z layer with its own slab of the v contraction indices.  piece_rows0(p) = first local row of piece p.
-int broadcast_and_update(cflx_chol* ch, int t, int jmin, bool below_only, double* X, cudaStream_t s) {
+int piece_ld(const cflx_chol* ch, int gfirst, int p) {  // leading dimension of piece p: its active rows, even, >= 2
+    const int rows = ch->Ml - first_local_tile(gfirst, p, ch->Px) * ch->v;
+    return (int)std::max<int64_t>(2, round_up(std::max(rows, 0), 2));
+}
+// Broadcast the Px pieces of the (transposed) panel of column block t (rows of global tiles >= gfirst) to every rank into
+// buffer set `buf`, and assemble the column operand for the local column tiles with global index >= jmin.
+int broadcast_pieces(cflx_chol* ch, int t, int gfirst, int jmin, int buf, cudaStream_t s) {
     const int v = ch->v, Px = ch->Px, Py = ch->Py, Pz = ch->Pz, Ml = ch->Ml, Nl = ch->Nl;
-    const int pi = ch->pi, pj = ch->pj, pk = ch->pk;
     const int pjt = t % Py;
-    const int gfirst = below_only ? t + 1 : t;  // first global tile row contained in the pieces
-    const int64_t ldg = ch->ldp;
-    const int64_t piece_stride = (int64_t)v * ldg;
+    const int64_t piece_stride = (int64_t)v * ch->ldp;
+    double* G = ch->G + (int64_t)buf * Px * piece_stride;
+    double* Bc = ch->Bc + (int64_t)buf * v * ch->ldb;
     if (ch->P > 1) {
         CFLX_NCCL(ncclGroupStart());
         for (int p = 0; p < Px; ++p) {
             const int rows = Ml - first_local_tile(gfirst, p, Px) * v;
             if (rows <= 0) continue;
             const int root = (p * Py + pjt) * Pz;
-            double* buf = ch->G + (int64_t)p * piece_stride;
-            const double* src = (ch->rank == root) ? ch->LT : buf;
-            CFLX_NCCL(ncclBroadcast(src, buf, (size_t)v * ldg, ncclDouble, root, ch->comm->world, s));
+            double* dst = G + (int64_t)p * piece_stride;
+            const double* src = (ch->rank == root) ? ch->LT : dst;
+            CFLX_NCCL(ncclBroadcast(src, dst, (size_t)v * piece_ld(ch, gfirst, p), ncclDouble, root, ch->comm->world, s));
         }
         CFLX_NCCL(ncclGroupEnd());
     } else {
-        CFLX_CUDA(cudaMemcpyAsync(ch->G, ch->LT, (size_t)v * ldg * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        CFLX_CUDA(cudaMemcpyAsync(G, ch->LT, (size_t)v * piece_ld(ch, gfirst, 0) * sizeof(double), cudaMemcpyDeviceToDevice, s));
     }
-    // columns: my local column tiles with global index >= jmin
-    const int lj0 = first_local_tile(jmin, pj, Py);
+    const int lj0 = first_local_tile(jmin, ch->pj, Py);
     const int ntc = Nl / v - lj0;
     if (ntc <= 0) return CFLX_OK;
-    GatherArgs ga{ch->G, ldg, piece_stride, ch->Bc, ch->ldb, v, Px, Py, pj, lj0, ntc, gfirst - 1};
+    GatherArgs ga{G, piece_stride, Bc, ch->ldb, v, Px, Py, ch->pj, lj0, ntc, gfirst, Ml};
     gather_cols_kernel<<<dim3(ntc, v), 128, 0, s>>>(ga);
     CFLX_CUDA(cudaGetLastError());
     ch->launches++;
-    const int my_first = first_local_tile(gfirst, pi, Px);  // first local tile row of MY piece
-    for (int tcol = 0; tcol < ntc; ++tcol) {
-        const int j = (lj0 + tcol) * Py + pj;                // global tile column
-        const int li = first_local_tile(j, pi, Px);          // first local tile row with global index >= j
+    return CFLX_OK;
+}
+// X[i][j] -= L[i][t] * L[j][t]^T on the local tiles with global tile row i >= tile column j, j in the local column tiles
+// [lj_lo, lj_hi) (global index >= jmin; lower triangle), each z layer with its own slab of the v contraction indices.
+int update_columns(cflx_chol* ch, int gfirst, int jmin, int buf, double* X, int lj_lo, int lj_hi, cudaStream_t s) {
+    const int v = ch->v, Px = ch->Px, Py = ch->Py, Ml = ch->Ml, Nl = ch->Nl;
+    const int pi = ch->pi, pj = ch->pj, pk = ch->pk;
+    const int64_t piece_stride = (int64_t)v * ch->ldp;
+    const double* G = ch->G + (int64_t)buf * Px * piece_stride;
+    const double* Bc = ch->Bc + (int64_t)buf * v * ch->ldb;
+    const int lj0 = first_local_tile(jmin, pj, Py);              // Bc column 0 corresponds to this local tile
+    const int my_first = first_local_tile(gfirst, pi, Px);        // first local tile row of MY piece
+    const int64_t ldg = piece_ld(ch, gfirst, pi);
+    for (int lj = std::max(lj_lo, lj0); lj < std::min(lj_hi, Nl / v); ++lj) {
+        const int j = lj * Py + pj;                               // global tile column
+        const int li = first_local_tile(j, pi, Px);               // first local tile row with global index >= j
         const int M = Ml - li * v;
         if (M <= 0) continue;
         GemmArgs g{};
         g.M = M; g.N = v; g.K = ch->nlayr;
-        g.AT = ch->G + (int64_t)pi * piece_stride + (int64_t)pk * ch->nlayr * ldg + (int64_t)(li - my_first) * v;
+        g.AT = G + (int64_t)pi * piece_stride + (int64_t)pk * ch->nlayr * ldg + (int64_t)(li - my_first) * v;
         g.ldat = ldg;
-        g.B = ch->Bc + (int64_t)pk * ch->nlayr * ch->ldb + (int64_t)tcol * v;
+        g.B = Bc + (int64_t)pk * ch->nlayr * ch->ldb + (int64_t)(lj - lj0) * v;
         g.ldb = ch->ldb;
-        g.C = X + (int64_t)li * v * Nl + (int64_t)(lj0 + tcol) * v;
+        g.C = X + (int64_t)li * v * Nl + (int64_t)lj * v;
         g.ldc = Nl;
         g.D = const_cast<double*>(g.C);
         g.ldd = Nl;
@@ -284,6 +310,59 @@ int broadcast_and_update(cflx_chol* ch, int t, int jmin, bool below_only, double
         ch->launches++;
     }
     return CFLX_OK;
+}
+int broadcast_and_update(cflx_chol* ch, int t, int jmin, bool below_only, double* X, cudaStream_t s) {
+    const int gfirst = below_only ? t + 1 : t;
+    CFLX_TRY(broadcast_pieces(ch, t, gfirst, jmin, 0, s));
+    return update_columns(ch, gfirst, jmin, 0, X, 0, ch->Nl / ch->v, s);
+}
+
+// Panel pipeline of step k on stream s: z-reduce of tile column k, Cholesky of the diagonal tile, L_kk^T down the grid
+// column, the panel solve, the stores, and (k < Kappa - 1) the broadcast of the panel pieces into buffer set k & 1.
+int panel_step(cflx_chol* ch, int k, cudaStream_t s) {
+    const int v = ch->v, Px = ch->Px, Py = ch->Py, Pz = ch->Pz, Ml = ch->Ml, Nl = ch->Nl;
+    const int pi = ch->pi, pj = ch->pj, pk = ch->pk;
+    const int pik = k % Px, pjk = k % Py;
+    const int loff = (k / Py) * v;
+    const int row0 = first_local_tile(k, pi, Px) * v;        // my first row at or below tile k
+    const int row1 = first_local_tile(k + 1, pi, Px) * v;    // ... strictly below tile k
+    const int n0 = Ml - row0, n1 = Ml - row1;
+    const int64_t ld = std::max<int64_t>(2, round_up(n0, 2));    // panel from the diagonal tile down
+    const int64_t ld1 = piece_ld(ch, k + 1, pi);                 // rows strictly below tile k (what is broadcast)
+    const bool on_col = (pj == pjk);
+    const bool owner = on_col && pi == pik && pk == 0;
+    const size_t psm = ((size_t)PB * (PB + 1) + (size_t)v * (PB + 1)) * sizeof(double);
+    // (4 of the previous step) tile column k summed over the z layers                  Cholesky.cpp:580-612
+    if (on_col && n0 > 0) {
+        CFLX_TRY(launch_extract_panel_T(ch->A11, Nl, row0, loff, n0, v, ch->PT, ld, s));
+        ch->launches++;
+        if (Pz > 1) CFLX_NCCL(ncclReduce(ch->PT, ch->PT, (size_t)v * ld, ncclDouble, ncclSum, 0, ch->k_comm.c, s));
+    }
+    // (1) Cholesky of the diagonal tile                                                 Cholesky.cpp:188-193
+    if (owner) {
+        tile_from_panel_kernel<<<(v * v + 255) / 256, 256, 0, s>>>(ch->PT, ld, v, ch->D);
+        potrf_tile_kernel<<<1, 1024, psm, s>>>(ch->D, v, ch->A00, ch->info + 1);
+        tile_store_kernel<<<(v * v + 255) / 256, 256, 0, s>>>(ch->D, v, ch->A11 + (int64_t)row0 * Nl + loff, Nl);
+        CFLX_CUDA(cudaGetLastError());
+        ch->launches += 3;
+    }
+    if (k == ch->Kappa - 1) return CFLX_OK;
+    // L_kk^T to the ranks that hold the tile column (layer 0)                           Cholesky.cpp:680-690
+    if (on_col && pk == 0 && Px > 1)
+        CFLX_NCCL(ncclBroadcast(ch->A00, ch->A00, (size_t)v * v, ncclDouble, pik, ch->i_comm.c, s));
+    // (2) tile column: A10 <- A10 * L_kk^-T                                              Cholesky.cpp:280-281,450-451
+    if (on_col && pk == 0 && n1 > 0) {
+        CFLX_TRY(launch_diag_inverses(ch->A00, v, ch->nb, ch->Uinv, ch->LinvT, s));
+        // PT rows are relative to row0 (ld); the solve works on the window below the diagonal tile and the result is
+        // repacked with the leading dimension of the broadcast piece (ld1)
+        CFLX_TRY(trsm_right_upper_T(ch->A00, ch->Uinv, v, ch->nb, ch->PT + (row1 - row0), ch->W, ld, n1, s));
+        CFLX_CUDA(cudaMemcpy2DAsync(ch->LT, ld1 * sizeof(double), ch->W, ld * sizeof(double), (size_t)n1 * sizeof(double), v,
+                                    cudaMemcpyDeviceToDevice, s));
+        CFLX_TRY(launch_store_panel_T(ch->A11, Nl, row1, loff, n1, v, ch->LT, ld1, s));
+        ch->launches += 2 * (v / ch->nb) + 1;
+    }
+    // the reference's A10 -> A01 representative exchange                                 Cholesky.cpp:205-330
+    return broadcast_pieces(ch, k, k + 1, k + 1, k & 1, s);
 }
 
 }  // namespace
@@ -401,18 +480,28 @@ int cflx_chol_create(cflx_comm* c, int N, int v, int Px, int Py, int Pz, cflx_ch
     ch->ldb = round_up(ch->Nl, 2) + 2;
 #define ALLOC(ptr, n) if ((rc = dmalloc(&(ptr), (n)))) return fail(rc)
     ALLOC(ch->A0, loc); ALLOC(ch->A11, loc);
-    ALLOC(ch->PT, (size_t)v * ch->ldp); ALLOC(ch->LT, (size_t)v * ch->ldp);
-    ALLOC(ch->G, (size_t)Px * v * ch->ldp); ALLOC(ch->Bc, (size_t)v * ch->ldb);
+    ALLOC(ch->PT, (size_t)v * ch->ldp); ALLOC(ch->LT, (size_t)v * ch->ldp); ALLOC(ch->W, (size_t)v * ch->ldp);
+    ALLOC(ch->G, 2 * (size_t)Px * v * ch->ldp); ALLOC(ch->Bc, 2 * (size_t)v * ch->ldb);
     ALLOC(ch->D, vv); ALLOC(ch->A00, vv); ALLOC(ch->Uinv, vv); ALLOC(ch->LinvT, vv); ALLOC(ch->acc, 4);
     ALLOC(ch->info, 4);
 #undef ALLOC
     cudaMemsetAsync(ch->PT, 0, (size_t)v * ch->ldp * sizeof(double), c->stream);
     cudaMemsetAsync(ch->LT, 0, (size_t)v * ch->ldp * sizeof(double), c->stream);
-    cudaMemsetAsync(ch->G, 0, (size_t)Px * v * ch->ldp * sizeof(double), c->stream);
-    cudaMemsetAsync(ch->Bc, 0, (size_t)v * ch->ldb * sizeof(double), c->stream);
+    cudaMemsetAsync(ch->W, 0, (size_t)v * ch->ldp * sizeof(double), c->stream);
+    cudaMemsetAsync(ch->G, 0, 2 * (size_t)Px * v * ch->ldp * sizeof(double), c->stream);
+    cudaMemsetAsync(ch->Bc, 0, 2 * (size_t)v * ch->ldb * sizeof(double), c->stream);
     cudaMemsetAsync(ch->A0, 0, loc * sizeof(double), c->stream);
     cudaMemsetAsync(ch->A00, 0, vv * sizeof(double), c->stream);
     if ((rc = gemm_tn_setup())) return fail(rc);
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&ch->side, cudaStreamNonBlocking, hi) != cudaSuccess) return fail(CFLX_ERR_CUDA);
+        for (int i = 0; i < 2; ++i)
+            if (cudaEventCreateWithFlags(&ch->ev_col[i], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ch->ev_panel[i], cudaEventDisableTiming) != cudaSuccess)
+                return fail(CFLX_ERR_CUDA);
+    }
     const size_t psm = ((size_t)PB * (PB + 1) + (size_t)v * (PB + 1)) * sizeof(double);
     if (cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm) != cudaSuccess) return fail(CFLX_ERR_CUDA);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(CFLX_ERR_CUDA);
@@ -449,8 +538,8 @@ int cflx_chol_factor(cflx_chol* ch, double* ms_out) {
     cflx_comm* c = ch->comm;
     cudaStream_t s = c->stream;
     CFLX_CUDA(cudaSetDevice(c->device));
-    const int v = ch->v, Px = ch->Px, Py = ch->Py, Pz = ch->Pz, Ml = ch->Ml, Nl = ch->Nl;
-    const int pi = ch->pi, pj = ch->pj, pk = ch->pk;
+    const int v = ch->v, Py = ch->Py, Ml = ch->Ml, Nl = ch->Nl;
+    const int pj = ch->pj;
     CFLX_CUDA(cudaMemcpyAsync(ch->A11, ch->A0, (size_t)Ml * Nl * sizeof(double), cudaMemcpyDeviceToDevice, s));
     CFLX_CUDA(cudaMemsetAsync(ch->info, 0, sizeof(int) * 4, s));
     CFLX_TRY(grid_barrier(c));
@@ -458,44 +547,27 @@ int cflx_chol_factor(cflx_chol* ch, double* ms_out) {
     CFLX_CUDA(cudaEventCreate(&e0));
     CFLX_CUDA(cudaEventCreate(&e1));
     CFLX_CUDA(cudaEventRecord(e0, s));
-    const size_t psm = ((size_t)PB * (PB + 1) + (size_t)v * (PB + 1)) * sizeof(double);
-    for (int k = 0; k < ch->Kappa; ++k) {
-        const int pik = k % Px, pjk = k % Py;
-        const int loff = (k / Py) * v;
-        const int row0 = first_local_tile(k, pi, Px) * v;        // my first row at or below tile k
-        const int row1 = first_local_tile(k + 1, pi, Px) * v;    // ... strictly below tile k
-        const int n0 = Ml - row0, n1 = Ml - row1;
-        const int64_t ld = ch->ldp;
-        const bool on_col = (pj == pjk);
-        const bool owner = on_col && pi == pik && pk == 0;
-        // (4 of the previous step) tile column k summed over the z layers                  Cholesky.cpp:580-612
-        if (on_col && n0 > 0) {
-            CFLX_TRY(launch_extract_panel_T(ch->A11, Nl, row0, loff, n0, v, ch->PT, ld, s));
-            ch->launches++;
-            if (Pz > 1) CFLX_NCCL(ncclReduce(ch->PT, ch->PT, (size_t)v * ld, ncclDouble, ncclSum, 0, ch->k_comm.c, s));
-        }
-        // (1) Cholesky of the diagonal tile                                                 Cholesky.cpp:188-193
-        if (owner) {
-            tile_from_panel_kernel<<<(v * v + 255) / 256, 256, 0, s>>>(ch->PT, ld, v, ch->D);
-            potrf_tile_kernel<<<1, 1024, psm, s>>>(ch->D, v, ch->A00, ch->info + 1);
-            tile_store_kernel<<<(v * v + 255) / 256, 256, 0, s>>>(ch->D, v, ch->A11 + (int64_t)row0 * Nl + loff, Nl);
-            CFLX_CUDA(cudaGetLastError());
-            ch->launches += 3;
-        }
-        if (k == ch->Kappa - 1) break;
-        // L_kk^T to the ranks that hold the tile column (layer 0)                           Cholesky.cpp:680-690
-        if (on_col && pk == 0 && Px > 1)
-            CFLX_NCCL(ncclBroadcast(ch->A00, ch->A00, (size_t)v * v, ncclDouble, pik, ch->i_comm.c, s));
-        // (2) tile column: A10 <- A10 * L_kk^-T                                              Cholesky.cpp:280-281,450-451
-        if (on_col && pk == 0 && n1 > 0) {
-            CFLX_TRY(launch_diag_inverses(ch->A00, v, ch->nb, ch->Uinv, ch->LinvT, s));
-            CFLX_TRY(trsm_right_upper_T(ch->A00, ch->Uinv, v, ch->nb, ch->PT + (row1 - row0), ch->LT, ld, n1, s));
-            CFLX_TRY(launch_store_panel_T(ch->A11, Nl, row1, loff, n1, v, ch->LT, ld, s));
-            ch->launches += 2 * (v / ch->nb) + 1;
-        }
-        // (3) trailing update with the panel pieces                                          Cholesky.cpp:345-351,512-544
-        CFLX_TRY(broadcast_and_update(ch, k, k + 1, true, ch->A11, s));
+    // Look-ahead: the panel pipeline of step k+1 (z-reduce, diagonal Cholesky, solve, piece broadcast -- and every NCCL
+    // call of the factorisation) runs on the side stream while the main stream applies the rank-v update of step k; the
+    // tile column of step k+1 is updated first so that the side stream can start.
+    cudaStream_t sp = ch->side;
+    CFLX_CUDA(cudaEventRecord(ch->ev_col[0], s));
+    CFLX_CUDA(cudaStreamWaitEvent(sp, ch->ev_col[0], 0));
+    CFLX_TRY(panel_step(ch, 0, sp));
+    CFLX_CUDA(cudaEventRecord(ch->ev_panel[0], sp));
+    for (int k = 0; k + 1 < ch->Kappa; ++k) {
+        const int b = k & 1, nb1 = (k + 1) & 1;
+        CFLX_CUDA(cudaStreamWaitEvent(s, ch->ev_panel[b], 0));             // pieces of step k are in buffer set b
+        const int ljn = (k + 1) / Py;                                        // local tile of column k+1 on its owners
+        const bool own_next = (pj == (k + 1) % Py);
+        if (own_next) CFLX_TRY(update_columns(ch, k + 1, k + 1, b, ch->A11, ljn, ljn + 1, s));
+        CFLX_CUDA(cudaEventRecord(ch->ev_col[nb1], s));
+        CFLX_CUDA(cudaStreamWaitEvent(sp, ch->ev_col[nb1], 0));
+        CFLX_TRY(panel_step(ch, k + 1, sp));
+        CFLX_CUDA(cudaEventRecord(ch->ev_panel[nb1], sp));
+        CFLX_TRY(update_columns(ch, k + 1, k + 1, b, ch->A11, own_next ? ljn + 1 : 0, Nl / v, s));
     }
+    CFLX_CUDA(cudaStreamWaitEvent(s, ch->ev_panel[(ch->Kappa - 1) & 1], 0));
     CFLX_CUDA(cudaEventRecord(e1, s));
     CFLX_CUDA(cudaEventSynchronize(e1));
     float ms = 0;
@@ -553,7 +625,8 @@ int cflx_chol_validate(cflx_chol* ch, double* abs_out, double* rel_out) {
         const int row0 = first_local_tile(t, ch->pi, Px) * v, n0 = Ml - row0;
         if (ch->pj == pjt && pk_save == 0 && n0 > 0) {
             dim3 grid((n0 + 31) / 32, (v + 31) / 32), block(32, 8);
-            extract_l_panel_T_kernel<<<grid, block, 0, s>>>(ch->A11, Nl, row0, (t / Py) * v, n0, v, Px, ch->pi, t, ch->LT, ch->ldp);
+            extract_l_panel_T_kernel<<<grid, block, 0, s>>>(ch->A11, Nl, row0, (t / Py) * v, n0, v, Px, ch->pi, t, ch->LT,
+                                                            piece_ld(ch, t, ch->pi));
         }
         // layer 0 applies the whole contraction, the other layers a zero-length slab (they only take part in the broadcasts)
         ch->nlayr = pk_save == 0 ? v : 0;
@@ -561,13 +634,13 @@ int cflx_chol_validate(cflx_chol* ch, double* abs_out, double* rel_out) {
         if (pk_save == 0) rc = broadcast_and_update(ch, t, t, false, R, s);
         else {
             // participate in the grouped broadcasts only
-            const int64_t ldg = ch->ldp;
             ncclGroupStart();
             for (int p = 0; p < Px && !rc; ++p) {
                 const int rows = Ml - first_local_tile(t, p, Px) * v;
                 if (rows <= 0) continue;
-                double* buf = ch->G + (int64_t)p * v * ldg;
-                if (ncclBroadcast(buf, buf, (size_t)v * ldg, ncclDouble, (p * Py + pjt) * ch->Pz, c->world, s) != ncclSuccess) rc = CFLX_ERR_NCCL;
+                double* buf = ch->G + (int64_t)p * v * ch->ldp;
+                if (ncclBroadcast(buf, buf, (size_t)v * piece_ld(ch, t, p), ncclDouble, (p * Py + pjt) * ch->Pz, c->world, s) != ncclSuccess)
+                    rc = CFLX_ERR_NCCL;
             }
             ncclGroupEnd();
         }

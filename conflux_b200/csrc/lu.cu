@@ -72,8 +72,13 @@ bool fixed_input_matrix(int n, std::vector<double>* out) {
     return false;
 }
 int pick_nb(int v) {  // block size of the diagonal inverses / TRSM sweeps (template instances: 128, 64, 32, 16, 8, 4)
+    static int cap = -1;  // CFLX_TRSM_NB caps the block size (A/B switch; default 128)
+    if (cap < 0) {
+        const char* e = getenv("CFLX_TRSM_NB");
+        cap = e ? atoi(e) : 128;
+    }
     for (int nb : {128, 64, 32, 16, 8, 4})
-        if (v % nb == 0) return nb;
+        if (nb <= cap && v % nb == 0) return nb;
     return 0;
 }
 }  // namespace

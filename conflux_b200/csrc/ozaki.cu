@@ -21,8 +21,8 @@
 //   warp 1     MMA issuer: one thread, UMMA 128 x (64..256) x 32 (up to four B planes per instruction), smem descriptors (SWIZZLE_128B, K-major), tcgen05.commit
 //              onto the mbarriers that free operand slots and publish finished accumulators;
 //   warp 2     TMEM allocation / release;
-//   warps 4-19 epilogue: tcgen05.ld 32x32b (lane = row), int32 -> FP64 recombination in registers, then a per-warp
-//              shared-memory patch turns "thread = row" into coalesced 64-byte row segments for the C read-modify-write.
+//   warps 4-19 epilogue: tcgen05.ld 16x256b (accumulator-fragment layout: four lanes = one 64-byte row segment), int32 ->
+//              FP64 recombination in registers, C read-modify-write straight from the registers (coalesced, no smem).
 // The 8 accumulators double as the pipeline between MMA and epilogue: group g of the next tile starts as soon as the
 // epilogue has drained group g of the current one.
 #include <cuda.h>
@@ -43,9 +43,8 @@ constexpr int OZ_A_SLOTS = 3;
 constexpr int OZ_A_BYTES = OZ_BM * OZ_KC, OZ_B_BYTES = OZ_BN * OZ_KC;
 constexpr int OZ_EPI_WARPS = 16;  // 4 per TMEM lane quadrant, 16 columns each
 constexpr int OZ_THREADS = 128 + 32 * OZ_EPI_WARPS;
-constexpr int OZ_PATCH_LD = 10;   // doubles per patch row (8 + 2 padding)
 constexpr size_t OZ_SMEM_OPERANDS = (size_t)2 * OZ_S * OZ_B_BYTES + (size_t)OZ_A_SLOTS * OZ_A_BYTES;
-constexpr size_t OZ_SMEM = 1024 /*alignment slack*/ + OZ_SMEM_OPERANDS + OZ_EPI_WARPS * 32 * OZ_PATCH_LD * sizeof(double) + 512 /*barriers*/;
+constexpr size_t OZ_SMEM = 1024 /*alignment slack*/ + OZ_SMEM_OPERANDS + 512 /*barriers*/;
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
@@ -69,6 +68,38 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, descriptors given as (low word, shared high word); ACC = true: D += A*B unconditionally
+template <bool ACC>
+__device__ __forceinline__ void umma_i8_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (ACC) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "setp.eq.u32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+            "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+            "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// 16 TMEM lanes x 16 columns in the accumulator-fragment layout (shape 16x256b, two 8-column repeats): thread T receives
+//   r[4*c8 + 0..1] = lane T/4,     columns 8*c8 + 2*(T%4) + {0, 1}
+//   r[4*c8 + 2..3] = lane T/4 + 8, same columns
+// i.e. four lanes cover one 64-byte row segment of 8 int32 -- the mapping a coalesced C access wants.
+__device__ __forceinline__ void tmem_ld_frag16(uint32_t taddr, int (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16]) {  // lane = thread, 16 consecutive columns
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -119,8 +150,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)oz_smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* sB = base;                                        // [2][8][64 x 128 B]
     unsigned char* sA = base + (size_t)2 * OZ_S * OZ_B_BYTES;         // [3][128 x 128 B]
-    double* patch = reinterpret_cast<double*>(base + OZ_SMEM_OPERANDS);  // [epilogue warps][32][OZ_PATCH_LD]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(patch + OZ_EPI_WARPS * 32 * OZ_PATCH_LD);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + OZ_SMEM_OPERANDS);
     uint64_t* fullB = bars;                 // [2][8]
     uint64_t* emptyB = bars + 16;           // [2][8]
     uint64_t* fullA = bars + 32;            // [3]
@@ -190,15 +220,23 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
     } else if (warp == 1) {
         // ================================================================== MMA issuer
+        // One CTA per SM owns all 512 TMEM columns, so the allocation starts at column 0 and every accumulator address is
+        // a compile-time constant; the plane loop is fully unrolled so that each UMMA is issued from immediates + two
+        // descriptor low words (the issue path of this single thread is what the tensor pipe waits for).
+        if (tmem_base != 0) __trap();
+        const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
+        constexpr uint32_t DESC_HI = (uint32_t)((((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61)) >> 32);
         uint32_t q = 0, acnt = 0, it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             for (int kc = 0; kc < KC; ++kc, ++q) {
                 const int set = q & 1;
                 const uint32_t useB = q >> 1;
+                const uint32_t b_lo = ((sB0 + (uint32_t)set * 8u * OZ_B_BYTES) & 0x3FFFF) >> 4;
+#pragma unroll
                 for (int s = 0; s < OZ_S; ++s, ++acnt) {
                     const int slot = acnt % OZ_A_SLOTS;
                     OZ_T0() mbar_wait(&fullA[slot], (acnt / OZ_A_SLOTS) & 1); OZ_T1(0)
-                    const uint64_t adesc = smem_desc_sw128(smem_u32(sA + (size_t)slot * OZ_A_BYTES));
+                    const uint32_t a_lo = ((sA0 + (uint32_t)slot * OZ_A_BYTES) & 0x3FFFF) >> 4;
                     if (s == 0) {  // row 0 touches every B plane and (first k chunk) every accumulator
                         for (int t = 0; t < OZ_S; ++t) {
                             OZ_T0() mbar_wait(&fullB[set * 8 + t], useB & 1); OZ_T1(1)
@@ -210,18 +248,17 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                         // The B planes t, t+1, ... of a set are contiguous 64-row tiles and their accumulators (groups s+t,
                         // s+t+1, ...) are contiguous 64-column blocks of tensor memory: up to four planes go through ONE
                         // UMMA of N = 64 * planes, so A_s is read from shared memory once per four products.
-                        for (int t = 0; t < OZ_S - s; t += 4) {
-                            const int np = min(4, OZ_S - s - t);
-                            const uint64_t bdesc = smem_desc_sw128(smem_u32(sB + (size_t)(set * 8 + t) * OZ_B_BYTES));
-                            const uint32_t d = tmem_base + (uint32_t)(s + t) * OZ_BN;
-                            const uint32_t idesc = oz_idesc(np * OZ_BN);
 #pragma unroll
-                            for (int k = 0; k < OZ_KC / 32; ++k)  // +32 bytes along K inside the swizzle atom: +2 in the descriptor
-                                umma_i8(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kc > 0 || s > 0 || k > 0) ? 1u : 0u);
+                        for (int t = 0; t < OZ_S - s; t += 4) {
+                            const int np = (OZ_S - s - t) < 4 ? (OZ_S - s - t) : 4;
+                            const uint32_t bt_lo = b_lo + (uint32_t)t * (OZ_B_BYTES >> 4);
+                            const uint32_t d = (uint32_t)(s + t) * OZ_BN;
+#pragma unroll
+                            for (int k = 0; k < OZ_KC / 32; ++k) {  // +32 bytes along K inside the swizzle atom: +2 in the descriptor
+                                if (s == 0 && k == 0) umma_i8_lo<false>(d, a_lo, bt_lo, DESC_HI, oz_idesc(np * OZ_BN), kc > 0 ? 1u : 0u);
+                                else umma_i8_lo<true>(d, a_lo + 2 * k, bt_lo + 2 * k, DESC_HI, oz_idesc(np * OZ_BN), 1u);
+                            }
                         }
-                    }
-                    __syncwarp();
-                    if (lane == 0) {
                         tc_commit(&emptyA[slot]);                         // plane s of A is consumed
                         tc_commit(&emptyB[set * 8 + (OZ_S - 1 - s)]);     // plane 7-s of B was used for the last time
                         if (kc == KC - 1) tc_commit(&tfull[s]);           // groups <= s are complete
@@ -232,10 +269,13 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
     } else if (warp >= 4) {
         // ================================================================== epilogue (16 warps)
+        // warp -> TMEM lane quadrant lq (32 rows) x 16-column quarter cq.  The accumulators are read in the fragment layout
+        // (tmem_ld_frag16): thread T holds rows {T/4, T/4+8, T/4+16, T/4+24} x column pairs {2(T%4), 8+2(T%4)}, so four
+        // lanes cover a 64-byte row segment and the C read-modify-write needs no shared-memory transpose.
         const int ew = warp - 4;
-        const int lq = warp & 3;             // TMEM lane quadrant this warp may access
-        const int cq = ew >> 2;              // 16-column quarter of the 64-wide tile
-        double* my_patch = patch + (size_t)ew * 32 * OZ_PATCH_LD;
+        const int lq = warp & 3;
+        const int cq = ew >> 2;
+        const int cp = lane & 3, r8 = lane >> 2;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int m0 = (tile / g.tiles_n) * OZ_BM, n0 = (tile % g.tiles_n) * OZ_BN;
@@ -243,72 +283,75 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 const int prow = m0 + lq * 32 + lane, pcol = n0 + cq * 16;
                 if (prow < g.M && pcol + 16 <= g.N) l2_prefetch_128(g.C + (int64_t)prow * g.ldc + pcol);
             }
-            // scales of my row and of the four column pairs I will store (needed only after the accumulators)
-            const int row = m0 + lq * 32 + lane;
-            const int colbase = n0 + cq * 16;
-            const int cp = lane & 3;                           // column pair inside an 8-column group
-            const double srow = (row < g.M) ? pow2i(g.ea[row] - 12) : 0.0;
-            double sc[2][2];
+            const int rowbase = m0 + lq * 32 + r8;             // my rows: rowbase + 8 * j, j = 0..3
+            const int colbase = n0 + cq * 16 + 2 * cp;          // my column pairs: colbase + 8 * c8
+            double srow[4], scol[2][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) srow[j] = (rowbase + 8 * j < g.M) ? pow2i(g.ea[rowbase + 8 * j] - 12) : 0.0;
 #pragma unroll
             for (int c8 = 0; c8 < 2; ++c8) {
-                const int col = colbase + c8 * 8 + 2 * cp;
-                sc[c8][0] = col < g.N ? pow2i(g.eb[g.b_row0 + col]) : 0.0;
-                sc[c8][1] = col < g.N ? pow2i(g.eb[g.b_row0 + col + 1]) : 0.0;
+                const int col = colbase + 8 * c8;
+                scol[c8][0] = col < g.N ? pow2i(g.eb[g.b_row0 + col]) : 0.0;
+                scol[c8][1] = col < g.N ? pow2i(g.eb[g.b_row0 + col + 1]) : 0.0;
             }
-            double sum[16];
+            // sum[h][i]: lane half h (rows 16h..16h+15 of the quadrant), i = 4*c8 + 2*rsel + x as delivered by tmem_ld_frag16
+            double sum[2][8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) sum[j] = 0.0;
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sum[h][i] = 0.0;
             double w = 1.0;
 #pragma unroll 1
             for (int grp = 0; grp < OZ_S; ++grp) {
                 OZ_T0() mbar_wait(&tfull[grp], it & 1); OZ_T1(0)
                 OZ_T0()
                 tc_fence_after();
-                int acc[16];
-                tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(grp * OZ_BN + cq * 16), acc);
+                int acc[2][8];
+                const uint32_t ta = ((uint32_t)(lq * 32) << 16) + (uint32_t)(grp * OZ_BN + cq * 16);
+                tmem_ld_frag16(ta, acc[0]);
+                tmem_ld_frag16(ta + (16u << 16), acc[1]);
+                tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[grp]);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    // exact int32 -> double without the conversion pipe: 2^52 + 2^31 + x, then subtract the bias
-                    const double x = __hiloint2double(0x43300000, acc[j] ^ 0x80000000) - 4503601774854144.0;
-                    sum[j] = fma(x, w, sum[j]);
-                }
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        // exact int32 -> double without the conversion pipe: 2^52 + 2^31 + x, then subtract the bias
+                        const double x = __hiloint2double(0x43300000, acc[h][i] ^ 0x80000000) - 4503601774854144.0;
+                        sum[h][i] = fma(x, w, sum[h][i]);
+                    }
                 w *= 0.0078125;  // 2^-7
                 OZ_T1(1)
             }
             OZ_T0()
-            // ---- C -= sum * 2^(ea + eb - 12), coalesced through the warp's patch: 8 columns at a time.  The C rows were
-            // pulled into L2 by the bulk prefetch issued at the top of the tile, so these loads see L2 latency only; the
-            // four loads of a column group are issued before its four stores.
+            // ---- C -= sum * 2^(ea - 12) * 2^eb straight from the registers; the four loads of a lane half are issued before its
+            // four stores (the C rows were pulled into L2 by the bulk prefetch at the top of the tile)
 #pragma unroll
-            for (int c8 = 0; c8 < 2; ++c8) {
-                const int col = colbase + c8 * 8 + 2 * cp;
-                const bool cok = col < g.N;
-                double2 cv[4];
+            for (int h = 0; h < 2; ++h) {
+                double2 cv[2][2];
 #pragma unroll
-                for (int rr = 0; rr < 4; ++rr) {
-                    const int r = m0 + lq * 32 + rr * 8 + (lane >> 2);
-                    cv[rr] = make_double2(0.0, 0.0);
-                    if (cok && r < g.M) cv[rr] = ld_c2(g.C + (int64_t)r * g.ldc + col);
-                }
-                const double s0 = sc[c8][0], s1 = sc[c8][1];
-                __syncwarp();
+                for (int rsel = 0; rsel < 2; ++rsel)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) my_patch[lane * OZ_PATCH_LD + j] = sum[c8 * 8 + j] * srow;
-                __syncwarp();
-#pragma unroll
-                for (int rr = 0; rr < 4; ++rr) {
-                    const int lr = rr * 8 + (lane >> 2);
-                    const int r = m0 + lq * 32 + lr;
-                    if (cok && r < g.M) {
-                        double2 c = cv[rr];
-                        c.x -= my_patch[lr * OZ_PATCH_LD + 2 * cp] * s0;
-                        c.y -= my_patch[lr * OZ_PATCH_LD + 2 * cp + 1] * s1;
-                        *reinterpret_cast<double2*>(g.C + (int64_t)r * g.ldc + col) = c;
+                    for (int c8 = 0; c8 < 2; ++c8) {
+                        const int r = rowbase + 16 * h + 8 * rsel, col = colbase + 8 * c8;
+                        cv[rsel][c8] = make_double2(0.0, 0.0);
+                        if (r < g.M && col < g.N) cv[rsel][c8] = ld_c2(g.C + (int64_t)r * g.ldc + col);
                     }
-                }
+#pragma unroll
+                for (int rsel = 0; rsel < 2; ++rsel)
+#pragma unroll
+                    for (int c8 = 0; c8 < 2; ++c8) {
+                        const int r = rowbase + 16 * h + 8 * rsel, col = colbase + 8 * c8;
+                        if (r < g.M && col < g.N) {
+                            const double sr = srow[2 * h + rsel];
+                            double2 c = cv[rsel][c8];
+                            c.x -= (sum[h][4 * c8 + 2 * rsel] * sr) * scol[c8][0];
+                            c.y -= (sum[h][4 * c8 + 2 * rsel + 1] * sr) * scol[c8][1];
+                            *reinterpret_cast<double2*>(g.C + (int64_t)r * g.ldc + col) = c;
+                        }
+                    }
             }
             OZ_T1(2)
         }

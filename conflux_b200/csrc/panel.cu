@@ -46,6 +46,7 @@ struct PanelArgs {
     uint2* slot_hdr;   // [2][MAXG][4]  LL words {payload32, epoch}: val_lo, val_hi, pos, row
     uint2* slot_rows;  // [2][MAXG][64] LL words: inner-block row of the candidate, two words per double
     int epoch_base;
+    int spec;          // G <= 32: warps 1..7 fetch every CTA's candidate row speculatively (else warp 0 fetches the winner's)
     long long* dbg;    // optional: 8 cycle counters of CTA 0 (cand+argmax, exchange, argmax2, row fetch, eliminate,
                        // load/write-back, U12 gather+solve, rank update)
 };
@@ -113,8 +114,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
     double* Ab = reinterpret_cast<double*>(smem_raw);  // [NB][Rpad] inner block, column-major per CTA
     double* U12 = Ab + (size_t)NB * p.Rpad;            // [NB][v]
     double* LU11 = U12 + (size_t)NB * p.v;             // [NB][NB+1] LU rows of this block's pivots
-    double* prow = LU11 + NB * (NB + 1);               // [2][NB] winner rows, double-buffered by column parity
-    unsigned long long* red_key = reinterpret_cast<unsigned long long*>(prow + 2 * NB);
+    double* prow = LU11 + NB * (NB + 1);               // [2][NB] winner rows, double-buffered by column parity (G > 32)
+    double* crow = prow + 2 * NB;                      // [2][32][NB] EVERY CTA's candidate row (G <= 32), by parity
+    unsigned long long* red_key = reinterpret_cast<unsigned long long*>(crow + 2 * 32 * NB);
     int* red_pos = reinterpret_cast<int*>(red_key + 2 * PT_WARPS);
     int* red_row = red_pos + 2 * PT_WARPS;
     int* pivrow_blk = red_row + 2 * PT_WARPS;  // [NB]
@@ -188,10 +190,13 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                                  : t == 2 ? (unsigned)mine.pos : (unsigned)mine.row;
                 st_ll(myhdr + t, w, epoch);
             }
-            if (mine.row >= 0 && t < nbc) {
-                const int lrw = mine.row - row_base;
-                double x = Ab[t * Rpad + lrw];
-                if (jprev >= 0 && t > jprev + 1) x = fma(-Ab[jprev * Rpad + lrw], pw[t], x);
+            if (t < nbc) {  // (zeros when this CTA has no active row left: the row words are fetched speculatively)
+                double x = 0.0;
+                if (mine.row >= 0) {
+                    const int lrw = mine.row - row_base;
+                    x = Ab[t * Rpad + lrw];
+                    if (jprev >= 0 && t > jprev + 1) x = fma(-Ab[jprev * Rpad + lrw], pw[t], x);
+                }
                 const unsigned long long xb = (unsigned long long)__double_as_longlong(x);
                 uint2* myrow = p.slot_rows + (size_t)(par * MAXG + cta) * 64 + 2 * t;
                 st_ll(myrow, (unsigned)xb, epoch);
@@ -243,6 +248,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                         win_sh[2 * par + 1] = w.row;
                     }
                 } else if (t < 32) {
+                    // warp 0: one header per lane -> warp-level argmax -> winner (no block barrier)
                     Cand gc{0ull, INT_MAX, -1};
                     if (t < p.G) {
                         const uint2* h = p.slot_hdr + (size_t)(par * MAXG + t) * 4;
@@ -257,20 +263,47 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                     const Cand w = warp_argmax(gc);
                     TICK(2)
                     // (w.row < 0 cannot happen while jg < nsteps = min(n, v): some row is still active)
-                    const int wcta = w.row / p.R;
-                    if (t < nbc) {
-                        const uint2* wr = p.slot_rows + (size_t)(par * MAXG + wcta) * 64 + 2 * t;
+                    if (!p.spec && t < nbc) {  // dependent fetch of the winner's row only
+                        const uint2* wr = p.slot_rows + (size_t)(par * MAXG + w.row / p.R) * 64 + 2 * t;
                         uint4 a;
                         do {
                             a = ld_ll2(wr);
                         } while (a.y != epoch || a.w != epoch);
-                        const double x = __longlong_as_double((long long)(((unsigned long long)a.z << 32) | a.x));
-                        pr[t] = x;
-                        LU11[j * (NB + 1) + t] = x;
+                        crow[(size_t)par * 32 * NB + (size_t)(w.row / p.R) * NB + t] =
+                            __longlong_as_double((long long)(((unsigned long long)a.z << 32) | a.x));
                     }
                     if (t == 0) {
                         win_sh[2 * par] = w.pos;
                         win_sh[2 * par + 1] = w.row;
+                    }
+                } else if (p.spec) {
+                    // warps 1..7: fetch EVERY CTA's candidate row speculatively, all loads of a lane in flight together, so
+                    // the winner's row costs no second dependent L2 round trip after the argmax
+                    double* cr = crow + (size_t)par * 32 * NB;
+                    constexpr int SPEC_T = PT_THREADS - 32;
+                    constexpr int SPEC_MAX = (32 * NB + SPEC_T - 1) / SPEC_T;
+                    const int e0 = t - 32, tot = p.G * nbc;
+                    uint4 a[SPEC_MAX];
+                    unsigned pending = 0;
+#pragma unroll
+                    for (int i = 0; i < SPEC_MAX; ++i)
+                        if (e0 + i * SPEC_T < tot) pending |= 1u << i;
+                    while (pending) {
+#pragma unroll
+                        for (int i = 0; i < SPEC_MAX; ++i) {
+                            if (pending & (1u << i)) {
+                                const int e = e0 + i * SPEC_T;
+                                a[i] = ld_ll2(p.slot_rows + (size_t)(par * MAXG + e / nbc) * 64 + 2 * (e % nbc));
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < SPEC_MAX; ++i) {
+                            if ((pending & (1u << i)) && a[i].y == epoch && a[i].w == epoch) {
+                                const int e = e0 + i * SPEC_T;
+                                cr[(e / nbc) * NB + e % nbc] = __longlong_as_double((long long)(((unsigned long long)a[i].z << 32) | a[i].x));
+                                pending &= ~(1u << i);
+                            }
+                        }
                     }
                 }
             }
@@ -279,6 +312,10 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
             win.key = 0;
             win.pos = win_sh[2 * par];
             win.row = win_sh[2 * par + 1];
+            if (p.G <= 32) {
+                pr = crow + (size_t)par * 32 * NB + (size_t)(win.row / p.R) * NB;
+                if (t < nbc) LU11[j * (NB + 1) + t] = pr[t];   // (read by phase C / the A00 emission, after later barriers)
+            }
             if (t == 0) {
                 pivrow_blk[j] = win.row;
                 if (cta == 0) p.perm_out[jg] = win.row;
@@ -456,7 +493,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
 
 template <int NB>
 size_t panel_smem_bytes(int Rpad, int v) {
-    return ((size_t)NB * Rpad + (size_t)NB * v + NB * (NB + 1) + 2 * NB) * sizeof(double) +
+    return ((size_t)NB * Rpad + (size_t)NB * v + NB * (NB + 1) + 2 * NB + 2 * 32 * NB) * sizeof(double) +
            2 * PT_WARPS * (sizeof(unsigned long long) + 2 * sizeof(int)) + (NB + 4) * sizeof(int) + (size_t)Rpad + 64;
 }
 
@@ -540,6 +577,14 @@ int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, 
     a.slot_hdr = reinterpret_cast<uint2*>(ws->slot_hdr);
     a.slot_rows = reinterpret_cast<uint2*>(ws->slot_rows);
     a.epoch_base = ws->epoch;
+    {
+        static int spec = -1;
+        if (spec < 0) {
+            const char* e = getenv("CFLX_PANEL_SPEC");
+            spec = e ? atoi(e) : 0;
+        }
+        a.spec = spec;
+    }
     a.dbg = ws->dbg;
     ws->epoch += v + 2 + (v & 1);  // keep the base even so slot parity == column parity
     const size_t budget = 222 * 1024;
