@@ -375,6 +375,9 @@ def main():
 
     # FP64 tensor-pipe peak of THIS GPU, measured before the runs (burst) -- MEASURED_PEAKS.json has no FP64 entry
     peak_burst = cb.dbg.fp64_peak_ex(0)[0] if rank == 0 else None
+    tcgen05 = bool(L.cflx_lu_uses_tcgen05(gv._h))
+    # raw int8 rate of the tensor pipe (back-to-back tcgen05.mma 128x256x32, operands resident): the ceiling of the tcgen05 path
+    i8_tmacs = cb.dbg.umma_peak(0, 256) if (rank == 0 and tcgen05) else None
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -430,7 +433,10 @@ def main():
         dmma_peak = peak_burst
         g_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         n1 = gv.Ml - gv.v                             # first-step shape of the trailing update (the ncu-captured launch)
-        traffic, traffic_src = load_traffic(n1, gv.Nl - gv.v, gv.nlayr, os.environ.get("CFLX_GEMM", "dmma"))
+        traffic, traffic_src = load_traffic(n1, gv.Nl - gv.v, gv.nlayr, "ozaki" if tcgen05 else "dmma")
+        # FP64-equivalent ceiling of the int8 path: 36 exact int8 plane products per FP64 product
+        i8_equiv = (2.0 * i8_tmacs / 36.0) if i8_tmacs else None
+        roof_peak = i8_equiv if tcgen05 else dmma_peak
         grid = (Px, Py, Pz)
         line = {
             "metric": "LU GFLOP/s (FP64, (2/3)N^3)", "value": value, "unit": "GFLOP/s", "n_gpus": args.gpus,
@@ -444,16 +450,24 @@ def main():
                     "d2h_bytes_per_step": int(gv.M * 4)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": os.environ.get("CFLX_GEMM", "dmma") + " trailing update",
-                         "achieved": g_tf, "peak": dmma_peak, "unit": "TFLOP/s", "frac": (g_tf / dmma_peak) if g_tf else None,
+            "roofline": {"bound": "tensor",
+                         "kernel": ("ozaki_gemm_kernel (int8 tcgen05.mma + TMEM + TMA, 36 exact digit-plane products per FP64 product)"
+                                    if tcgen05 else "gemm_tn_kernel (FP64 DMMA.8x8x4)") + ", trailing update",
+                         "achieved": g_tf, "peak": roof_peak, "unit": "TFLOP/s (FP64-equivalent)" if tcgen05 else "TFLOP/s",
+                         "frac": (g_tf / roof_peak) if (g_tf and roof_peak) else None,
+                         "frac_of_fp64_dmma_peak": (g_tf / dmma_peak) if g_tf else None, "fp64_dmma_peak": dmma_peak,
+                         "int8_pipe_measured_pops": (2.0 * i8_tmacs / 1e3) if i8_tmacs else None,
                          # dram__bytes_read+write of ONE launch of the first-step shape, read from the committed summary of
                          # an `ncu --set full` capture; algorithmic bytes = 16*M*N + 8*K*(M+N) (C read+write, operands once)
                          "traffic": traffic, "traffic_source": traffic_src,
                          "traffic_launch": f"M={n1} N={gv.Nl - gv.v} K={gv.nlayr} (step 0), algorithmic "
                                            f"{16.0 * n1 * (gv.Nl - gv.v) + 8.0 * gv.nlayr * (n1 + gv.Nl - gv.v):.4g} B",
-                         "peak_source": "FP64 tensor (DMMA.8x8x4) burst peak measured live on this GPU by cflx_dbg_fp64_peak_ex "
+                         "peak_source": ("tcgen05 path: peak = raw int8 rate of the tensor pipe measured live (cflx_dbg_umma_peak: back-to-back "
+                                         "tcgen05.mma.kind::i8 128x256x32, one CTA per SM; nominal 4.5 POP/s) x 2 / 36 digit-plane products; "
+                                         if tcgen05 else "") +
+                                        "fp64_dmma_peak = FP64 tensor (DMMA.8x8x4) burst peak measured live by cflx_dbg_fp64_peak_ex "
                                         "(best ~2 ms launch; = 148 SM x 4 x 32 flop/clk x 1.965 GHz); MEASURED_PEAKS.json has no "
-                                        "FP64 entry; nominal %.0f TFLOP/s" % FP64_TENSOR_NOMINAL_TFLOPS,
+                                        "FP64 / int8 entry; nominal FP64 %.0f TFLOP/s" % FP64_TENSOR_NOMINAL_TFLOPS,
                          "share_of_step": gemm_ms / dev_ms if dev_ms else None,
                          "whole_path_frac": value / 1e3 / (args.gpus * dmma_peak)},
             "parity": {"permutation_is_permutation": bool(ok_perm), "pivots_equal_reference": pivots_equal,

@@ -728,9 +728,11 @@ int cflx_lu_create(cflx_comm* c, int M, int N, int v, int Px, int Py, int Pz, cf
     if ((rc = panel_workspace_create(&lu->pws))) return fail(rc);
     if ((rc = gemm_tn_setup())) return fail(rc);
     {
-        // CFLX_GEMM=ozaki: trailing update on the int8 tcgen05 path (needs whole 128-element k chunks per layer)
+        // Trailing update on the int8 tcgen05 path (ozaki.cu) whenever the layer's contraction length is a whole number
+        // of 128-element k chunks (v = 256 / 512 of the BASELINE configs); CFLX_GEMM=dmma selects the FP64 DMMA anchor.
         const char* e = getenv("CFLX_GEMM");
-        if (e && !strcmp(e, "ozaki") && lu->nlayr % 128 == 0 && lu->nlayr <= 512) {
+        const bool want = !(e && !strcmp(e, "dmma"));
+        if (want && lu->nlayr % 128 == 0 && lu->nlayr <= 512) {
             if ((rc = ozaki_workspace_create(&lu->oz, lu->Ml, lu->Nl, lu->nlayr))) return fail(rc);
             lu->use_ozaki = true;
         }
@@ -945,6 +947,7 @@ int cflx_host_free(void* p) {
     return CFLX_OK;
 }
 
+int cflx_lu_uses_tcgen05(const cflx_lu* lu) { return lu && lu->use_ozaki ? 1 : 0; }
 int cflx_lu_launch_count(cflx_lu* lu, int64_t* count_out, int reset) {
     if (!lu || !count_out) return CFLX_ERR_ARG;
     *count_out = lu->launches;

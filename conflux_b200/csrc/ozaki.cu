@@ -16,15 +16,15 @@
 // Kernel structure (one CTA per SM, 640 threads, all 512 TMEM columns):
 //   warp 0     TMA producer: digit planes are K-major int8 ([plane][row][K], 128-byte swizzled boxes of 128 k) fetched
 //              with cp.async.bulk.tensor.3d through two tensor maps; per 128-k chunk the 8 B planes stay resident
-//              (double-buffered set) while the 8 A planes stream through a 3-slot ring: every plane chunk is loaded
-//              exactly once per tile;
+//              (double-buffered set, ONE barrier pair per set) while the 8 A planes stream through a ring of three
+//              two-plane slots: every plane chunk is loaded exactly once per tile;
 //   warp 1     MMA issuer: one thread, UMMA 128 x (64..256) x 32 (up to four B planes per instruction), smem descriptors (SWIZZLE_128B, K-major), tcgen05.commit
 //              onto the mbarriers that free operand slots and publish finished accumulators;
 //   warp 2     TMEM allocation / release;
 //   warps 4-19 epilogue: tcgen05.ld 16x256b (accumulator-fragment layout: four lanes = one 64-byte row segment), int32 ->
 //              FP64 recombination in registers, C read-modify-write straight from the registers (coalesced, no smem).
-// The 8 accumulators double as the pipeline between MMA and epilogue: group g of the next tile starts as soon as the
-// epilogue has drained group g of the current one.
+// The 8 accumulators are the pipeline between MMA and epilogue: the epilogue drains group g while the MMAs of the later
+// groups still run, and the C update of a tile overlaps the MMAs of the next one.
 #include <cuda.h>
 
 #include <algorithm>
@@ -39,11 +39,12 @@ namespace cflx {
 namespace {
 constexpr int OZ_S = 8;           // digit planes per operand
 constexpr int OZ_BM = 128, OZ_BN = 64, OZ_KC = 128;  // CTA tile, k-chunk (bytes = int8 elements)
-constexpr int OZ_A_SLOTS = 3;
+constexpr int OZ_A_SLOTS = 3;      // each slot holds TWO consecutive A planes (one full/empty barrier pair per two rows)
 constexpr int OZ_A_BYTES = OZ_BM * OZ_KC, OZ_B_BYTES = OZ_BN * OZ_KC;
+constexpr int OZ_A_SLOT_BYTES = 2 * OZ_A_BYTES;
 constexpr int OZ_EPI_WARPS = 16;  // 4 per TMEM lane quadrant, 16 columns each
 constexpr int OZ_THREADS = 128 + 32 * OZ_EPI_WARPS;
-constexpr size_t OZ_SMEM_OPERANDS = (size_t)2 * OZ_S * OZ_B_BYTES + (size_t)OZ_A_SLOTS * OZ_A_BYTES;
+constexpr size_t OZ_SMEM_OPERANDS = (size_t)2 * OZ_S * OZ_B_BYTES + (size_t)OZ_A_SLOTS * OZ_A_SLOT_BYTES;
 constexpr size_t OZ_SMEM = 1024 /*alignment slack*/ + OZ_SMEM_OPERANDS + 512 /*barriers*/;
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -131,6 +132,11 @@ __device__ __forceinline__ double2 ld_c2(const double* p) {
 __device__ __forceinline__ void l2_prefetch_128(const void* p) {  // 16-byte aligned, 128 bytes
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], 128;" ::"l"(p) : "memory");
 }
+__host__ __device__ constexpr double pow2c(int e) {  // compile-time 2^e, e <= 0
+    double x = 1.0;
+    for (int i = 0; i < -e; ++i) x *= 0.5;
+    return x;
+}
 __device__ __forceinline__ double pow2i(int e) { return __longlong_as_double((long long)(1023 + e) << 52); }  // |e| < 1022
 
 struct OzArgs {
@@ -144,6 +150,7 @@ struct OzArgs {
     long long* dbg;        // optional [16] cycle counters of CTA 0: see cflx_dbg_ozaki_cycles
 };
 
+template <bool DBG>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, OzArgs g) {
     extern __shared__ unsigned char oz_smem_raw[];
@@ -151,20 +158,20 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     unsigned char* sB = base;                                        // [2][8][64 x 128 B]
     unsigned char* sA = base + (size_t)2 * OZ_S * OZ_B_BYTES;         // [3][128 x 128 B]
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + OZ_SMEM_OPERANDS);
-    uint64_t* fullB = bars;                 // [2][8]
-    uint64_t* emptyB = bars + 16;           // [2][8]
-    uint64_t* fullA = bars + 32;            // [3]
-    uint64_t* emptyA = bars + 35;           // [3]
-    uint64_t* tfull = bars + 38;            // [8]
-    uint64_t* tempty = bars + 46;           // [8]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 54);
+    uint64_t* fullB = bars;                 // [2]  one per B set (8 planes land on it)
+    uint64_t* emptyB = bars + 2;            // [2]
+    uint64_t* fullA = bars + 4;             // [3]  one per A slot (2 planes)
+    uint64_t* emptyA = bars + 7;            // [3]
+    uint64_t* tfull = bars + 10;            // [8]  accumulator (group) g is complete
+    uint64_t* tdone = bars + 18;            // [1]  the epilogue has drained all 8 accumulators of the tile
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = g.tiles_m * g.tiles_n;
     const int KC = g.K / OZ_KC;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 2; ++i) {
             mbar_init(&fullB[i], 1);
             mbar_init(&emptyB[i], 1);
         }
@@ -172,10 +179,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             mbar_init(&fullA[i], 1);
             mbar_init(&emptyA[i], 1);
         }
-        for (int i = 0; i < OZ_S; ++i) {
-            mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], OZ_EPI_WARPS);  // one arrival per epilogue warp
-        }
+        for (int i = 0; i < OZ_S; ++i) mbar_init(&tfull[i], 1);
+        mbar_init(tdone, OZ_EPI_WARPS);  // one arrival per epilogue warp
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -189,31 +194,31 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 
     long long tm[4] = {0, 0, 0, 0};
     long long tc0 = 0;
-#define OZ_T0() if (g.dbg) tc0 = clock64();
-#define OZ_T1(i) if (g.dbg) tm[i] += clock64() - tc0;
-    const long long t_begin = g.dbg ? clock64() : 0;
+#define OZ_T0() if constexpr (DBG) tc0 = clock64();
+#define OZ_T1(i) if constexpr (DBG) tm[i] += clock64() - tc0;
+    const long long t_begin = DBG ? clock64() : 0;
     if (warp == 0) {
         // ================================================================== TMA producer
-        uint32_t q = 0, acnt = 0;  // k-chunks and A planes loaded so far by this CTA
+        uint32_t q = 0, acnt = 0;  // k-chunks and A slots (plane pairs) loaded so far by this CTA
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int m0 = (tile / g.tiles_n) * OZ_BM, n0 = (tile % g.tiles_n) * OZ_BN;
             for (int kc = 0; kc < KC; ++kc, ++q) {
                 const int set = q & 1;
                 const uint32_t useB = q >> 1;
-                for (int t = 0; t < OZ_S; ++t) {
-                    OZ_T0() mbar_wait(&emptyB[set * 8 + t], (useB & 1) ^ 1); OZ_T1(0)
-                    if (lane == 0) {
-                        mbar_arrive_expect_tx(&fullB[set * 8 + t], OZ_B_BYTES);
-                        tma_load_3d(sB + (size_t)(set * 8 + t) * OZ_B_BYTES, &mapB, kc * OZ_KC, g.b_row0 + n0, t, &fullB[set * 8 + t]);
-                    }
+                OZ_T0() mbar_wait(&emptyB[set], (useB & 1) ^ 1); OZ_T1(0)
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&fullB[set], OZ_S * OZ_B_BYTES);
+                    for (int t = 0; t < OZ_S; ++t)
+                        tma_load_3d(sB + (size_t)(set * 8 + t) * OZ_B_BYTES, &mapB, kc * OZ_KC, g.b_row0 + n0, t, &fullB[set]);
                 }
-                for (int s = 0; s < OZ_S; ++s, ++acnt) {
+                for (int sp = 0; sp < OZ_S / 2; ++sp, ++acnt) {
                     const int slot = acnt % OZ_A_SLOTS;
                     const uint32_t useA = acnt / OZ_A_SLOTS;
                     OZ_T0() mbar_wait(&emptyA[slot], (useA & 1) ^ 1); OZ_T1(1)
                     if (lane == 0) {
-                        mbar_arrive_expect_tx(&fullA[slot], OZ_A_BYTES);
-                        tma_load_3d(sA + (size_t)slot * OZ_A_BYTES, &mapA, kc * OZ_KC, m0, s, &fullA[slot]);
+                        mbar_arrive_expect_tx(&fullA[slot], OZ_A_SLOT_BYTES);
+                        tma_load_3d(sA + (size_t)slot * OZ_A_SLOT_BYTES, &mapA, kc * OZ_KC, m0, 2 * sp, &fullA[slot]);
+                        tma_load_3d(sA + (size_t)slot * OZ_A_SLOT_BYTES + OZ_A_BYTES, &mapA, kc * OZ_KC, m0, 2 * sp + 1, &fullA[slot]);
                     }
                 }
             }
@@ -232,36 +237,36 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 const int set = q & 1;
                 const uint32_t useB = q >> 1;
                 const uint32_t b_lo = ((sB0 + (uint32_t)set * 8u * OZ_B_BYTES) & 0x3FFFF) >> 4;
+                OZ_T0() mbar_wait(&fullB[set], useB & 1); OZ_T1(1)
+                OZ_T0() if (kc == 0) mbar_wait(tdone, (it & 1) ^ 1); OZ_T1(2)   // the epilogue drained the previous tile
 #pragma unroll
-                for (int s = 0; s < OZ_S; ++s, ++acnt) {
+                for (int sp = 0; sp < OZ_S / 2; ++sp, ++acnt) {
                     const int slot = acnt % OZ_A_SLOTS;
                     OZ_T0() mbar_wait(&fullA[slot], (acnt / OZ_A_SLOTS) & 1); OZ_T1(0)
-                    const uint32_t a_lo = ((sA0 + (uint32_t)slot * OZ_A_BYTES) & 0x3FFFF) >> 4;
-                    if (s == 0) {  // row 0 touches every B plane and (first k chunk) every accumulator
-                        for (int t = 0; t < OZ_S; ++t) {
-                            OZ_T0() mbar_wait(&fullB[set * 8 + t], useB & 1); OZ_T1(1)
-                            OZ_T0() if (kc == 0) mbar_wait(&tempty[t], (it & 1) ^ 1); OZ_T1(2)  // epilogue drained this accumulator
-                        }
-                    }
                     tc_fence_after();
                     if (lane == 0) {
-                        // The B planes t, t+1, ... of a set are contiguous 64-row tiles and their accumulators (groups s+t,
-                        // s+t+1, ...) are contiguous 64-column blocks of tensor memory: up to four planes go through ONE
-                        // UMMA of N = 64 * planes, so A_s is read from shared memory once per four products.
 #pragma unroll
-                        for (int t = 0; t < OZ_S - s; t += 4) {
-                            const int np = (OZ_S - s - t) < 4 ? (OZ_S - s - t) : 4;
-                            const uint32_t bt_lo = b_lo + (uint32_t)t * (OZ_B_BYTES >> 4);
-                            const uint32_t d = (uint32_t)(s + t) * OZ_BN;
+                        for (int half = 0; half < 2; ++half) {
+                            const int s = 2 * sp + half;
+                            const uint32_t a_lo = ((sA0 + (uint32_t)slot * OZ_A_SLOT_BYTES + (uint32_t)half * OZ_A_BYTES) & 0x3FFFF) >> 4;
+                            // The B planes t, t+1, ... of a set are contiguous 64-row tiles and their accumulators (groups
+                            // s+t, s+t+1, ...) are contiguous 64-column blocks of tensor memory: up to four planes go through
+                            // ONE UMMA of N = 64 * planes, so A_s is read from shared memory once per four products.
 #pragma unroll
-                            for (int k = 0; k < OZ_KC / 32; ++k) {  // +32 bytes along K inside the swizzle atom: +2 in the descriptor
-                                if (s == 0 && k == 0) umma_i8_lo<false>(d, a_lo, bt_lo, DESC_HI, oz_idesc(np * OZ_BN), kc > 0 ? 1u : 0u);
-                                else umma_i8_lo<true>(d, a_lo + 2 * k, bt_lo + 2 * k, DESC_HI, oz_idesc(np * OZ_BN), 1u);
+                            for (int t = 0; t < OZ_S - s; t += 4) {
+                                const int np = (OZ_S - s - t) < 4 ? (OZ_S - s - t) : 4;
+                                const uint32_t bt_lo = b_lo + (uint32_t)t * (OZ_B_BYTES >> 4);
+                                const uint32_t d = (uint32_t)(s + t) * OZ_BN;
+#pragma unroll
+                                for (int k = 0; k < OZ_KC / 32; ++k) {  // +32 bytes along K inside the swizzle atom: +2 in the descriptor
+                                    if (s == 0 && k == 0) umma_i8_lo<false>(d, a_lo, bt_lo, DESC_HI, oz_idesc(np * OZ_BN), kc > 0 ? 1u : 0u);
+                                    else umma_i8_lo<true>(d, a_lo + 2 * k, bt_lo + 2 * k, DESC_HI, oz_idesc(np * OZ_BN), 1u);
+                                }
                             }
+                            if (kc == KC - 1) tc_commit(&tfull[s]);       // groups <= s are complete
                         }
-                        tc_commit(&emptyA[slot]);                         // plane s of A is consumed
-                        tc_commit(&emptyB[set * 8 + (OZ_S - 1 - s)]);     // plane 7-s of B was used for the last time
-                        if (kc == KC - 1) tc_commit(&tfull[s]);           // groups <= s are complete
+                        tc_commit(&emptyA[slot]);                         // planes 2sp, 2sp+1 of A are consumed
+                        if (sp == OZ_S / 2 - 1) tc_commit(&emptyB[set]);  // the whole B set of this k chunk is consumed
                     }
                     __syncwarp();
                 }
@@ -285,14 +290,15 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             }
             const int rowbase = m0 + lq * 32 + r8;             // my rows: rowbase + 8 * j, j = 0..3
             const int colbase = n0 + cq * 16 + 2 * cp;          // my column pairs: colbase + 8 * c8
-            double srow[4], scol[2][2];
+            // exponents of my 4 rows and 4 columns (kept as ints: half the registers; the powers of two are rebuilt at use)
+            int erow[4], ecol[2][2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) srow[j] = (rowbase + 8 * j < g.M) ? pow2i(g.ea[rowbase + 8 * j] - 12) : 0.0;
+            for (int j = 0; j < 4; ++j) erow[j] = (rowbase + 8 * j < g.M) ? g.ea[rowbase + 8 * j] - 12 : 0;
 #pragma unroll
             for (int c8 = 0; c8 < 2; ++c8) {
                 const int col = colbase + 8 * c8;
-                scol[c8][0] = col < g.N ? pow2i(g.eb[g.b_row0 + col]) : 0.0;
-                scol[c8][1] = col < g.N ? pow2i(g.eb[g.b_row0 + col + 1]) : 0.0;
+                ecol[c8][0] = col < g.N ? g.eb[g.b_row0 + col] : 0;
+                ecol[c8][1] = col < g.N ? g.eb[g.b_row0 + col + 1] : 0;
             }
             // sum[h][i]: lane half h (rows 16h..16h+15 of the quadrant), i = 4*c8 + 2*rsel + x as delivered by tmem_ld_frag16
             double sum[2][8];
@@ -300,30 +306,47 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) sum[h][i] = 0.0;
-            double w = 1.0;
-#pragma unroll 1
-            for (int grp = 0; grp < OZ_S; ++grp) {
-                OZ_T0() mbar_wait(&tfull[grp], it & 1); OZ_T1(0)
+            // 16 half-steps (group g, lane half h), two 8-register buffers: the TMEM load of the NEXT half-step is issued
+            // right after the current one has landed and BEFORE its FP64 work, so load latency and recombination overlap.
+            int acc[2][8];
+            const uint32_t ta0 = ((uint32_t)(lq * 32) << 16) + (uint32_t)(cq * 16);
+            OZ_T0() mbar_wait(&tfull[0], it & 1); OZ_T1(0)
+            tc_fence_after();
+            tmem_ld_frag16(ta0, acc[0]);
+#pragma unroll
+            for (int step = 0; step < 2 * OZ_S; ++step) {
+                const int grp = step >> 1, h = step & 1;
                 OZ_T0()
-                tc_fence_after();
-                int acc[2][8];
-                const uint32_t ta = ((uint32_t)(lq * 32) << 16) + (uint32_t)(grp * OZ_BN + cq * 16);
-                tmem_ld_frag16(ta, acc[0]);
-                tmem_ld_frag16(ta + (16u << 16), acc[1]);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[grp]);
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        // exact int32 -> double without the conversion pipe: 2^52 + 2^31 + x, then subtract the bias
-                        const double x = __hiloint2double(0x43300000, acc[h][i] ^ 0x80000000) - 4503601774854144.0;
-                        sum[h][i] = fma(x, w, sum[h][i]);
+                tmem_ld_wait();                                  // acc[step & 1] has landed
+                bool issued = true;
+                if (step + 1 < 2 * OZ_S) {
+                    const uint32_t tn = ta0 + (uint32_t)(((step + 1) >> 1) * OZ_BN) + ((uint32_t)(((step + 1) & 1) * 16) << 16);
+                    if (h == 0) {
+                        tmem_ld_frag16(tn, acc[(step + 1) & 1]);  // other lane half of the same group
+                    } else if (mbar_test(&tfull[grp + 1], it & 1)) {
+                        tc_fence_after();
+                        tmem_ld_frag16(tn, acc[(step + 1) & 1]);  // next group is already complete
+                    } else {
+                        issued = false;
                     }
-                w *= 0.0078125;  // 2^-7
+                } else {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tdone);            // all 8 accumulators are in registers
+                }
+                const double w = pow2c(-7 * grp);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    // exact int32 -> double without the conversion pipe: 2^52 + 2^31 + x, then subtract the bias
+                    const double x = __hiloint2double(0x43300000, acc[step & 1][i] ^ 0x80000000) - 4503601774854144.0;
+                    sum[h][i] = fma(x, w, sum[h][i]);
+                }
                 OZ_T1(1)
+                if (!issued) {
+                    OZ_T0() mbar_wait(&tfull[grp + 1], it & 1); OZ_T1(0)
+                    tc_fence_after();
+                    tmem_ld_frag16(ta0 + (uint32_t)((grp + 1) * OZ_BN), acc[(step + 1) & 1]);
+                }
             }
             OZ_T0()
             // ---- C -= sum * 2^(ea - 12) * 2^eb straight from the registers; the four loads of a lane half are issued before its
@@ -345,10 +368,10 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                     for (int c8 = 0; c8 < 2; ++c8) {
                         const int r = rowbase + 16 * h + 8 * rsel, col = colbase + 8 * c8;
                         if (r < g.M && col < g.N) {
-                            const double sr = srow[2 * h + rsel];
+                            const double sr = pow2i(erow[2 * h + rsel]);
                             double2 c = cv[rsel][c8];
-                            c.x -= (sum[h][4 * c8 + 2 * rsel] * sr) * scol[c8][0];
-                            c.y -= (sum[h][4 * c8 + 2 * rsel + 1] * sr) * scol[c8][1];
+                            c.x -= (sum[h][4 * c8 + 2 * rsel] * sr) * pow2i(ecol[c8][0]);
+                            c.y -= (sum[h][4 * c8 + 2 * rsel + 1] * sr) * pow2i(ecol[c8][1]);
                             *reinterpret_cast<double2*>(g.C + (int64_t)r * g.ldc + col) = c;
                         }
                     }
@@ -356,7 +379,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             OZ_T1(2)
         }
     }
-    if (g.dbg && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 4)) {
+    if (DBG && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 4)) {
         const int o = warp == 0 ? 0 : (warp == 1 ? 4 : 8);
         for (int i = 0; i < 3; ++i) g.dbg[o + i] = tm[i];
         g.dbg[o + 3] = clock64() - t_begin;
@@ -533,8 +556,10 @@ int ozaki_workspace_create(OzakiWorkspace* ws, int max_rows, int max_cols, int K
     CFLX_TRY(make_plane_map(&ws->maps->a, ws->planesA, K, ws->cap_a, OZ_BM));
     CFLX_TRY(make_plane_map(&ws->maps->b, ws->planesB, K, ws->cap_b, OZ_BN));
     static PerDeviceMax cfg;
-    if (cfg.raise(OZ_SMEM))
-        CFLX_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
+    if (cfg.raise(OZ_SMEM)) {
+        CFLX_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
+        CFLX_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
+    }
     int dev = 0;
     CFLX_CUDA(cudaGetDevice(&dev));
     CFLX_CUDA(cudaDeviceGetAttribute(&ws->sms, cudaDevAttrMultiProcessorCount, dev));
@@ -617,7 +642,8 @@ int launch_ozaki_gemm(OzakiWorkspace* ws, int M, int N, int col0, double* C, int
     int cap = ws->sms;
     if (max_ctas > 0 && max_ctas < cap) cap = max_ctas;
     if (grid > cap) grid = cap;
-    ozaki_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM, s>>>(ws->maps->a, ws->maps->b, g);
+    if (ws->dbg) ozaki_gemm_kernel<true><<<grid, OZ_THREADS, OZ_SMEM, s>>>(ws->maps->a, ws->maps->b, g);
+    else ozaki_gemm_kernel<false><<<grid, OZ_THREADS, OZ_SMEM, s>>>(ws->maps->a, ws->maps->b, g);
     CFLX_CUDA(cudaGetLastError());
     return CFLX_OK;
 }

@@ -89,6 +89,8 @@ int cflx_lu_get_permutation(cflx_lu*, int* permutation_out);
 int cflx_lu_validate(cflx_lu*, double* frob_abs_out, double* frob_rel_out);
 /* COLLECTIVE.  = cflx_lu_validate(lu, NULL, rel_out) */
 int cflx_lu_residual(cflx_lu*, double* rel_out);
+/* 1 when this plan's trailing update runs on the int8 tcgen05 path (ozaki.cu), 0 for the FP64 DMMA kernel (gemm.cu) */
+int cflx_lu_uses_tcgen05(const cflx_lu*);
 /* number of kernels this plan launched since the last call (for bench.py's gpu_launches) */
 int cflx_lu_launch_count(cflx_lu*, int64_t* count_out, int reset);
 /* per-phase device time of the last cflx_lu_factor when profiling was enabled: ms_out[8] =

@@ -8,11 +8,11 @@ run() { # name, env...
   env "$@" timeout 600 $TR bench.py --gpus 4 --steps 3 --warmup 3 > gpurun_out/n4_bench_$name.log 2> gpurun_out/n4_bench_$name.err; echo "bench $name rc=$?"
 }
 run default CFLX_X=0
-run ozaki CFLX_GEMM=ozaki
+run dmma CFLX_GEMM=dmma
 run cap32 CFLX_PANEL_CTAS=32
-run ozaki_cap32 CFLX_GEMM=ozaki CFLX_PANEL_CTAS=32
+run dmma_cap32 CFLX_GEMM=dmma CFLX_PANEL_CTAS=32
 timeout 300 $TR tools/timeline.py --gpus 4 --out gpurun_out/n4_timeline.json > gpurun_out/n4_timeline.log 2>&1; echo "timeline rc=$?"
-CFLX_GEMM=ozaki timeout 300 $TR tools/timeline.py --gpus 4 --out gpurun_out/n4_timeline_ozaki.json >> gpurun_out/n4_timeline.log 2>&1; echo "timeline(ozaki) rc=$?"
+CFLX_GEMM=dmma timeout 300 $TR tools/timeline.py --gpus 4 --out gpurun_out/n4_timeline_dmma.json >> gpurun_out/n4_timeline.log 2>&1; echo "timeline(ozaki) rc=$?"
 timeout 600 $TR bench.py --algo cholesky --gpus 4 --steps 2 --warmup 3 > gpurun_out/n4_chol.log 2> gpurun_out/n4_chol.err; echo "chol bench rc=$?"
 python - <<'PY'
 import json, glob

@@ -39,7 +39,7 @@ tl = cb.timeline(gv)
 _lib.lib().cflx_lu_set_profiling(gv._h, 0)
 rec = {"workload": f"LU N={gv.N} v={gv.v} grid {g[0]}x{g[1]}x{g[2]}", "rank": gv.rank, "coords": [gv.pi, gv.pj, gv.pk],
        "mode": "serialising timers" if a.mode == 1 else "event pairs on the launching streams (not serialised)",
-       "factor_ms_unprofiled": ms_plain, "factor_ms_profiled": ms, "gemm": os.environ.get("CFLX_GEMM", "dmma"), "regions": tl}
+       "factor_ms_unprofiled": ms_plain, "factor_ms_profiled": ms, "gemm": "ozaki (int8 tcgen05)" if _lib.lib().cflx_lu_uses_tcgen05(gv._h) else "dmma", "regions": tl}
 out = a.out or ""
 if out:
     path = out.replace(".json", f"_rank{gv.rank}.json") if world > 1 else out
