@@ -35,6 +35,8 @@ struct cflx_chol {
            *W = nullptr, *Uinv = nullptr, *LinvT = nullptr, *acc = nullptr;
     int* info = nullptr;
     int64_t ldp = 0, ldb = 0;
+    OzakiWorkspace oz{};                    // digit planes of the int8 tcgen05 rank-v update (default when v / Pz is 128..512)
+    bool use_ozaki = false;
     cudaStream_t side = nullptr;            // panel pipeline of step k+1 (all NCCL traffic lives here) under the update of step k
     cudaEvent_t ev_col[2] = {nullptr, nullptr}, ev_panel[2] = {nullptr, nullptr};
     bool have_input = false, factored = false;
@@ -231,6 +233,7 @@ void free_chol(cflx_chol* ch) {
     cudaSetDevice(ch->comm->device);
     for (double* p : {ch->A0, ch->A11, ch->PT, ch->LT, ch->W, ch->G, ch->Bc, ch->D, ch->A00, ch->Uinv, ch->LinvT, ch->acc}) cudaFree(p);
     cudaFree(ch->info);
+    if (ch->use_ozaki) ozaki_workspace_destroy(&ch->oz);
     if (ch->side) cudaStreamDestroy(ch->side);
     for (int i = 0; i < 2; ++i) {
         if (ch->ev_col[i]) cudaEventDestroy(ch->ev_col[i]);
@@ -281,7 +284,7 @@ int broadcast_pieces(cflx_chol* ch, int t, int gfirst, int jmin, int buf, cudaSt
 }
 // X[i][j] -= L[i][t] * L[j][t]^T on the local tiles with global tile row i >= tile column j, j in the local column tiles
 // [lj_lo, lj_hi) (global index >= jmin; lower triangle), each z layer with its own slab of the v contraction indices.
-int update_columns(cflx_chol* ch, int gfirst, int jmin, int buf, double* X, int lj_lo, int lj_hi, cudaStream_t s) {
+int update_columns(cflx_chol* ch, int gfirst, int jmin, int buf, double* X, int lj_lo, int lj_hi, cudaStream_t s, int planes_buf = -1) {
     const int v = ch->v, Px = ch->Px, Py = ch->Py, Ml = ch->Ml, Nl = ch->Nl;
     const int pi = ch->pi, pj = ch->pj, pk = ch->pk;
     const int64_t piece_stride = (int64_t)v * ch->ldp;
@@ -290,13 +293,20 @@ int update_columns(cflx_chol* ch, int gfirst, int jmin, int buf, double* X, int 
     const int lj0 = first_local_tile(jmin, pj, Py);              // Bc column 0 corresponds to this local tile
     const int my_first = first_local_tile(gfirst, pi, Px);        // first local tile row of MY piece
     const int64_t ldg = piece_ld(ch, gfirst, pi);
-    for (int lj = std::max(lj_lo, lj0); lj < std::min(lj_hi, Nl / v); ++lj) {
-        const int j = lj * Py + pj;                               // global tile column
+    // One launch per GROUP of local tile columns: wide enough (>= ~8192 rows x columns of v) to fill the machine; the rows
+    // start at the diagonal of the group's first column, so later columns of a group also update a few tiles above their
+    // own diagonal (upper triangle: never read) -- a few per cent of extra flops instead of many half-empty launches.
+    const int lj_end = std::min(lj_hi, Nl / v);
+    const int my_rows = Ml - my_first * v;                          // rows of my piece = rows of the A planes
+    for (int lj = std::max(lj_lo, lj0); lj < lj_end;) {
+        const int j = lj * Py + pj;                               // global tile column of the group's first column
         const int li = first_local_tile(j, pi, Px);               // first local tile row with global index >= j
         const int M = Ml - li * v;
-        if (M <= 0) continue;
+        if (M <= 0) break;                                        // later columns have even fewer rows
+        int gcols = std::max(1, (8192 + M - 1) / M);
+        gcols = std::min(gcols, lj_end - lj);
         GemmArgs g{};
-        g.M = M; g.N = v; g.K = ch->nlayr;
+        g.M = M; g.N = gcols * v; g.K = ch->nlayr;
         g.AT = G + (int64_t)pi * piece_stride + (int64_t)pk * ch->nlayr * ldg + (int64_t)(li - my_first) * v;
         g.ldat = ldg;
         g.B = Bc + (int64_t)pk * ch->nlayr * ch->ldb + (int64_t)(lj - lj0) * v;
@@ -306,9 +316,31 @@ int update_columns(cflx_chol* ch, int gfirst, int jmin, int buf, double* X, int 
         g.D = const_cast<double*>(g.C);
         g.ldd = Nl;
         g.alpha = -1.0; g.beta = 1.0;
-        CFLX_TRY(launch_gemm_tn(g, s));
+        if (ch->use_ozaki && planes_buf == buf)   // planes of this buffer set are current (see split_planes)
+            CFLX_TRY(launch_ozaki_gemm(&ch->oz, M, g.N, (li - my_first) * v, (lj - lj0) * v, g.D, Nl, ch->oz.sms - 8, s));
+        else
+            CFLX_TRY(launch_gemm_tn(g, s));
         ch->launches++;
+        lj += gcols;
     }
+    (void)my_rows;
+    return CFLX_OK;
+}
+// digit planes of the operands of one update sweep: my piece (rows) and the gathered column operand, this layer's slab
+int split_planes(cflx_chol* ch, int gfirst, int jmin, int buf, cudaStream_t s);
+int split_planes(cflx_chol* ch, int gfirst, int jmin, int buf, cudaStream_t s) {
+    if (!ch->use_ozaki) return CFLX_OK;
+    const int v = ch->v, Px = ch->Px;
+    const int64_t piece_stride = (int64_t)v * ch->ldp;
+    const double* G = ch->G + (int64_t)buf * Px * piece_stride;
+    const double* Bc = ch->Bc + (int64_t)buf * v * ch->ldb;
+    const int my_first = first_local_tile(gfirst, ch->pi, Px);
+    const int rows = ch->Ml - my_first * v;
+    const int ncols = ch->Nl - first_local_tile(jmin, ch->pj, ch->Py) * v;
+    const int64_t ldg = piece_ld(ch, gfirst, ch->pi);
+    if (rows > 0) CFLX_TRY(ozaki_split_a(&ch->oz, G + (int64_t)ch->pi * piece_stride + (int64_t)ch->pk * ch->nlayr * ldg, ldg, rows, s));
+    if (ncols > 0) CFLX_TRY(ozaki_split_b(&ch->oz, Bc + (int64_t)ch->pk * ch->nlayr * ch->ldb, ch->ldb, 0, ncols, s));
+    ch->launches += 2;
     return CFLX_OK;
 }
 int broadcast_and_update(cflx_chol* ch, int t, int jmin, bool below_only, double* X, cudaStream_t s) {
@@ -494,6 +526,13 @@ int cflx_chol_create(cflx_comm* c, int N, int v, int Px, int Py, int Pz, cflx_ch
     cudaMemsetAsync(ch->A00, 0, vv * sizeof(double), c->stream);
     if ((rc = gemm_tn_setup())) return fail(rc);
     {
+        const char* e = getenv("CFLX_GEMM");
+        if (!(e && !strcmp(e, "dmma")) && ch->nlayr % 128 == 0 && ch->nlayr <= 512) {
+            if ((rc = ozaki_workspace_create(&ch->oz, ch->Ml, ch->Nl, ch->nlayr))) return fail(rc);
+            ch->use_ozaki = true;
+        }
+    }
+    {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if (cudaStreamCreateWithPriority(&ch->side, cudaStreamNonBlocking, hi) != cudaSuccess) return fail(CFLX_ERR_CUDA);
@@ -558,14 +597,15 @@ int cflx_chol_factor(cflx_chol* ch, double* ms_out) {
     for (int k = 0; k + 1 < ch->Kappa; ++k) {
         const int b = k & 1, nb1 = (k + 1) & 1;
         CFLX_CUDA(cudaStreamWaitEvent(s, ch->ev_panel[b], 0));             // pieces of step k are in buffer set b
+        CFLX_TRY(split_planes(ch, k + 1, k + 1, b, s));                     // (int8 tcgen05 path) digit planes of both operands
         const int ljn = (k + 1) / Py;                                        // local tile of column k+1 on its owners
         const bool own_next = (pj == (k + 1) % Py);
-        if (own_next) CFLX_TRY(update_columns(ch, k + 1, k + 1, b, ch->A11, ljn, ljn + 1, s));
+        if (own_next) CFLX_TRY(update_columns(ch, k + 1, k + 1, b, ch->A11, ljn, ljn + 1, s, b));
         CFLX_CUDA(cudaEventRecord(ch->ev_col[nb1], s));
         CFLX_CUDA(cudaStreamWaitEvent(sp, ch->ev_col[nb1], 0));
         CFLX_TRY(panel_step(ch, k + 1, sp));
         CFLX_CUDA(cudaEventRecord(ch->ev_panel[nb1], sp));
-        CFLX_TRY(update_columns(ch, k + 1, k + 1, b, ch->A11, own_next ? ljn + 1 : 0, Nl / v, s));
+        CFLX_TRY(update_columns(ch, k + 1, k + 1, b, ch->A11, own_next ? ljn + 1 : 0, Nl / v, s, b));
     }
     CFLX_CUDA(cudaStreamWaitEvent(s, ch->ev_panel[(ch->Kappa - 1) & 1], 0));
     CFLX_CUDA(cudaEventRecord(e1, s));

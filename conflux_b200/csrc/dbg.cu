@@ -336,7 +336,7 @@ int cflx_dbg_ozaki_gemm(int M, int N, int K, const double* AT, const double* B, 
         rc = ozaki_split_a(&ws, dA.as<double>(), ldat, M, 0);
         if (!rc) rc = ozaki_split_b(&ws, dB.as<double>(), ldb, 0, N, 0);
         cudaEventRecord(e1);
-        if (!rc) rc = launch_ozaki_gemm(&ws, M, N, 0, dC.as<double>(), ldc, 0, 0);
+        if (!rc) rc = launch_ozaki_gemm(&ws, M, N, 0, 0, dC.as<double>(), ldc, 0, 0);
         cudaEventRecord(e2);
         if (cudaEventSynchronize(e2) != cudaSuccess) {
             set_last_error("ozaki kernel failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -40,7 +40,7 @@ void ozaki_workspace_destroy(OzakiWorkspace* ws);
 int ozaki_split_a(OzakiWorkspace* ws, const double* LT, int64_t ld, int n, cudaStream_t s);
 int ozaki_split_b(OzakiWorkspace* ws, const double* U, int64_t ld, int col0, int n, cudaStream_t s);
 int umma_peak_probe(int n, int use_f16, double* tmacs_out);
-int launch_ozaki_gemm(OzakiWorkspace* ws, int M, int N, int col0, double* C, int64_t ldc, int max_ctas, cudaStream_t s);
+int launch_ozaki_gemm(OzakiWorkspace* ws, int M, int N, int row0, int col0, double* C, int64_t ldc, int max_ctas, cudaStream_t s);
 
 // ---------------------------------------------------------------- panel.cu
 // Partial-pivot LU of the n x v panel stored TRANSPOSED in W (W[c][r], ld = ldw), in place, rows never move:

@@ -317,7 +317,7 @@ int trailing_gemm(cflx_lu* lu, int k, int part, int fnpr, int n_act, int col_lo,
     g.beta = 1.0;
     const int e = 4 * k + 2 * part;
     if (lu->time_gemm) CFLX_CUDA(cudaEventRecord(lu->ev[e], s));
-    if (lu->use_ozaki) CFLX_TRY(launch_ozaki_gemm(&lu->oz, g.M, g.N, u_col_off, g.D, g.ldd, max_ctas, s));
+    if (lu->use_ozaki) CFLX_TRY(launch_ozaki_gemm(&lu->oz, g.M, g.N, 0, u_col_off, g.D, g.ldd, max_ctas, s));
     else CFLX_TRY(launch_gemm_tn(g, s));
     if (lu->time_gemm) CFLX_CUDA(cudaEventRecord(lu->ev[e + 1], s));
     lu->ev_used[e / 2] = lu->time_gemm;

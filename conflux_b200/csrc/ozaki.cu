@@ -21,8 +21,9 @@
 //   warp 1     MMA issuer: one thread, UMMA 128 x (64..256) x 32 (up to four B planes per instruction), smem descriptors (SWIZZLE_128B, K-major), tcgen05.commit
 //              onto the mbarriers that free operand slots and publish finished accumulators;
 //   warp 2     TMEM allocation / release;
-//   warps 4-19 epilogue: tcgen05.ld 16x256b (accumulator-fragment layout: four lanes = one 64-byte row segment), int32 ->
-//              FP64 recombination in registers, C read-modify-write straight from the registers (coalesced, no smem).
+//   warps 4-19 epilogue: tcgen05.ld 16x256b (accumulator-fragment layout), software-pipelined int32 -> FP64 recombination in
+//              registers; the negated update is staged in shared memory and ADDED to C by the L2 through bulk reduce
+//              operations (cp.reduce.async.bulk .add.f64, SASS UBLKRED): the SM never reads C.
 // The 8 accumulators are the pipeline between MMA and epilogue: the epilogue drains group g while the MMAs of the later
 // groups still run, and the C update of a tile overlaps the MMAs of the next one.
 #include <cuda.h>
@@ -39,13 +40,14 @@ namespace cflx {
 namespace {
 constexpr int OZ_S = 8;           // digit planes per operand
 constexpr int OZ_BM = 128, OZ_BN = 64, OZ_KC = 128;  // CTA tile, k-chunk (bytes = int8 elements)
-constexpr int OZ_A_SLOTS = 3;      // each slot holds TWO consecutive A planes (one full/empty barrier pair per two rows)
+constexpr int OZ_A_SLOTS = 2;      // each slot holds TWO consecutive A planes (one full/empty barrier pair per two rows)
 constexpr int OZ_A_BYTES = OZ_BM * OZ_KC, OZ_B_BYTES = OZ_BN * OZ_KC;
 constexpr int OZ_A_SLOT_BYTES = 2 * OZ_A_BYTES;
 constexpr int OZ_EPI_WARPS = 16;  // 4 per TMEM lane quadrant, 16 columns each
 constexpr int OZ_THREADS = 128 + 32 * OZ_EPI_WARPS;
 constexpr size_t OZ_SMEM_OPERANDS = (size_t)2 * OZ_S * OZ_B_BYTES + (size_t)OZ_A_SLOTS * OZ_A_SLOT_BYTES;
-constexpr size_t OZ_SMEM = 1024 /*alignment slack*/ + OZ_SMEM_OPERANDS + 512 /*barriers*/;
+constexpr int OZ_STAGE_DOUBLES = 16 * OZ_BN;   // per TMEM lane quadrant: 16 rows x 64 columns of (-update), source of the bulk reduce-add
+constexpr size_t OZ_SMEM = 1024 /*alignment slack*/ + OZ_SMEM_OPERANDS + (size_t)4 * OZ_STAGE_DOUBLES * sizeof(double) + 512 /*barriers*/;
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
@@ -122,13 +124,16 @@ __host__ __device__ constexpr uint32_t oz_idesc(int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
 }
 
-// coherent 16-byte load of C without a memory clobber: free to be scheduled ahead of stores to OTHER elements (every
-// element is read once, by the thread that later writes it), see gemm.cu
-__device__ __forceinline__ double2 ld_c2(const double* p) {
-    double2 v;
-    asm("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
+// C[...] += smem[...] (FP64, round-to-nearest) done by the L2 through the TMA engine (SASS UBLKRED.ADD.F64): no C load, no
+// load latency on the SM; bytes a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_reduce_add_f64(double* gdst, const double* ssrc, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
 }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void l2_prefetch_128(const void* p) {  // 16-byte aligned, 128 bytes
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], 128;" ::"l"(p) : "memory");
 }
@@ -141,6 +146,7 @@ __device__ __forceinline__ double pow2i(int e) { return __longlong_as_double((lo
 
 struct OzArgs {
     int M, N, K;           // C is M x N, K = contraction length (multiple of 128)
+    int a_row0;            // first row of the A planes that belongs to row 0 of this C window
     int b_row0;            // first row of the B planes that belongs to column 0 of this C window
     double* C;             // in place: C -= A^T-planes * B-planes
     int64_t ldc;
@@ -157,11 +163,12 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)oz_smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* sB = base;                                        // [2][8][64 x 128 B]
     unsigned char* sA = base + (size_t)2 * OZ_S * OZ_B_BYTES;         // [3][128 x 128 B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + OZ_SMEM_OPERANDS);
+    double* stage = reinterpret_cast<double*>(base + OZ_SMEM_OPERANDS);   // [4 lane quadrants][16 rows][64 columns]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 4 * OZ_STAGE_DOUBLES);
     uint64_t* fullB = bars;                 // [2]  one per B set (8 planes land on it)
     uint64_t* emptyB = bars + 2;            // [2]
-    uint64_t* fullA = bars + 4;             // [3]  one per A slot (2 planes)
-    uint64_t* emptyA = bars + 7;            // [3]
+    uint64_t* fullA = bars + 4;             // [2..3]  one per A slot (2 planes)
+    uint64_t* emptyA = bars + 7;            // [2..3]
     uint64_t* tfull = bars + 10;            // [8]  accumulator (group) g is complete
     uint64_t* tdone = bars + 18;            // [1]  the epilogue has drained all 8 accumulators of the tile
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
@@ -217,8 +224,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                     OZ_T0() mbar_wait(&emptyA[slot], (useA & 1) ^ 1); OZ_T1(1)
                     if (lane == 0) {
                         mbar_arrive_expect_tx(&fullA[slot], OZ_A_SLOT_BYTES);
-                        tma_load_3d(sA + (size_t)slot * OZ_A_SLOT_BYTES, &mapA, kc * OZ_KC, m0, 2 * sp, &fullA[slot]);
-                        tma_load_3d(sA + (size_t)slot * OZ_A_SLOT_BYTES + OZ_A_BYTES, &mapA, kc * OZ_KC, m0, 2 * sp + 1, &fullA[slot]);
+                        tma_load_3d(sA + (size_t)slot * OZ_A_SLOT_BYTES, &mapA, kc * OZ_KC, g.a_row0 + m0, 2 * sp, &fullA[slot]);
+                        tma_load_3d(sA + (size_t)slot * OZ_A_SLOT_BYTES + OZ_A_BYTES, &mapA, kc * OZ_KC, g.a_row0 + m0, 2 * sp + 1, &fullA[slot]);
                     }
                 }
             }
@@ -293,7 +300,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             // exponents of my 4 rows and 4 columns (kept as ints: half the registers; the powers of two are rebuilt at use)
             int erow[4], ecol[2][2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) erow[j] = (rowbase + 8 * j < g.M) ? g.ea[rowbase + 8 * j] - 12 : 0;
+            for (int j = 0; j < 4; ++j) erow[j] = (rowbase + 8 * j < g.M) ? g.ea[g.a_row0 + rowbase + 8 * j] - 12 : 0;
 #pragma unroll
             for (int c8 = 0; c8 < 2; ++c8) {
                 const int col = colbase + 8 * c8;
@@ -349,32 +356,37 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 }
             }
             OZ_T0()
-            // ---- C -= sum * 2^(ea - 12) * 2^eb straight from the registers; the four loads of a lane half are issued before its
-            // four stores (the C rows were pulled into L2 by the bulk prefetch at the top of the tile)
+            // ---- C -= sum * 2^(ea - 12) * 2^eb: the NEGATED update is staged in shared memory (16 rows x 16 columns per lane
+            // half) and added to C by the L2 through a bulk reduce (one 128-byte row segment per lane): the SM never loads C
+            // (the rows were pulled into L2 by the prefetch at the top of the tile).
+            // The four warps of a lane quadrant share one 16-row x 64-column staging tile, so that ONE bulk reduce moves a whole
+            // 512-byte row segment (the TMA engine's cost is per operation: 128 operations per tile instead of 512).
+            double* stg = stage + (size_t)lq * OZ_STAGE_DOUBLES;
+            const int segcols = min(OZ_BN, g.N - n0);            // valid columns of the tile (even)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                double2 cv[2][2];
+                bulk_wait_read();                                 // my previous reduces have read their staging rows
+                named_bar_sync(1 + lq, 128);                      // ... and so have those of the other three warps
 #pragma unroll
-                for (int rsel = 0; rsel < 2; ++rsel)
-#pragma unroll
-                    for (int c8 = 0; c8 < 2; ++c8) {
-                        const int r = rowbase + 16 * h + 8 * rsel, col = colbase + 8 * c8;
-                        cv[rsel][c8] = make_double2(0.0, 0.0);
-                        if (r < g.M && col < g.N) cv[rsel][c8] = ld_c2(g.C + (int64_t)r * g.ldc + col);
-                    }
-#pragma unroll
-                for (int rsel = 0; rsel < 2; ++rsel)
+                for (int rsel = 0; rsel < 2; ++rsel) {
+                    const double sr = -pow2i(erow[2 * h + rsel]);
 #pragma unroll
                     for (int c8 = 0; c8 < 2; ++c8) {
-                        const int r = rowbase + 16 * h + 8 * rsel, col = colbase + 8 * c8;
-                        if (r < g.M && col < g.N) {
-                            const double sr = pow2i(erow[2 * h + rsel]);
-                            double2 c = cv[rsel][c8];
-                            c.x -= (sum[h][4 * c8 + 2 * rsel] * sr) * pow2i(ecol[c8][0]);
-                            c.y -= (sum[h][4 * c8 + 2 * rsel + 1] * sr) * pow2i(ecol[c8][1]);
-                            *reinterpret_cast<double2*>(g.C + (int64_t)r * g.ldc + col) = c;
-                        }
+                        double2 o;
+                        o.x = (sum[h][4 * c8 + 2 * rsel] * sr) * pow2i(ecol[c8][0]);
+                        o.y = (sum[h][4 * c8 + 2 * rsel + 1] * sr) * pow2i(ecol[c8][1]);
+                        *reinterpret_cast<double2*>(stg + (8 * rsel + r8) * OZ_BN + cq * 16 + 8 * c8 + 2 * cp) = o;
                     }
+                }
+                fence_proxy_async();
+                named_bar_sync(1 + lq, 128);                      // the whole 16 x 64 tile is staged
+                if (lane < 4) {                                   // warp cq issues rows 4cq .. 4cq+3 of this half
+                    const int lr = 4 * cq + lane;
+                    const int r = m0 + lq * 32 + 16 * h + lr;
+                    if (r < g.M && segcols > 0)
+                        bulk_reduce_add_f64(g.C + (int64_t)r * g.ldc + n0, stg + lr * OZ_BN, (uint32_t)segcols * 8u);
+                    bulk_commit();
+                }
             }
             OZ_T1(2)
         }
@@ -386,6 +398,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
 #undef OZ_T0
 #undef OZ_T1
+    if (warp >= 4) bulk_wait_all();   // every reduce-add of this thread has been performed
     tc_fence_before();
     __syncthreads();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -623,15 +636,16 @@ int ozaki_split_b(OzakiWorkspace* ws, const double* U, int64_t ld, int col0, int
     CFLX_CUDA(cudaGetLastError());
     return CFLX_OK;
 }
-// C[0..M) x [0..N) -= (rows 0..M of the A planes) * (rows col0..col0+N of the B planes)
-int launch_ozaki_gemm(OzakiWorkspace* ws, int M, int N, int col0, double* C, int64_t ldc, int max_ctas, cudaStream_t s) {
+// C[0..M) x [0..N) -= (rows row0..row0+M of the A planes) * (rows col0..col0+N of the B planes)
+int launch_ozaki_gemm(OzakiWorkspace* ws, int M, int N, int row0, int col0, double* C, int64_t ldc, int max_ctas, cudaStream_t s) {
     if (M <= 0 || N <= 0) return CFLX_OK;
-    if ((N & 1) || (ldc & 1) || col0 < 0 || M > ws->cap_a || col0 + N > ws->cap_b) {
-        set_last_error("ozaki_gemm: unsupported window M=%d N=%d col0=%d ldc=%lld", M, N, col0, (long long)ldc);
+    if ((N & 1) || (ldc & 1) || col0 < 0 || row0 < 0 || row0 + M > ws->cap_a || col0 + N > ws->cap_b) {
+        set_last_error("ozaki_gemm: unsupported window M=%d N=%d row0=%d col0=%d ldc=%lld", M, N, row0, col0, (long long)ldc);
         return CFLX_ERR_UNSUPPORTED;
     }
     OzArgs g{};
     g.M = M; g.N = N; g.K = ws->K;
+    g.a_row0 = row0;
     g.b_row0 = col0;
     g.C = C; g.ldc = ldc;
     g.ea = ws->ea; g.eb = ws->eb;

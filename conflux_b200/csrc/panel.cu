@@ -61,6 +61,25 @@ __device__ __forceinline__ uint4 ld_ll2(const uint2* p) {  // two consecutive LL
     return v;
 }
 
+// ---- cluster variant (small panels): the LL slots live in the SHARED MEMORY of every CTA of one thread-block cluster;
+// a candidate is published with remote shared-memory stores (DSMEM, ~200 cycles) into all peers and every CTA polls its
+// own shared memory -- no L2 round trip, no cluster barrier per column.
+constexpr int CS_MAX = 8;  // portable cluster size
+__device__ __forceinline__ void st_ll_dsmem(const uint2* local_slot, unsigned peer, unsigned data, unsigned epoch) {
+    unsigned remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_slot)), "r"(peer));
+    asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(remote), "r"(data), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ uint4 ld_ll2_smem(const uint2* p) {  // two consecutive LL words of my own shared memory
+    uint4 v;
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 struct Cand {
     unsigned long long key;  // bits of |a| (monotone for non-negative doubles)
     int pos;                 // LAPACK position (tie-break: smaller wins); INT_MAX = no candidate
@@ -108,7 +127,7 @@ __device__ __forceinline__ Cand block_argmax(Cand c, unsigned long long* red_key
     return best;
 }
 
-template <int NB, int RPT_MAX>
+template <int NB, int RPT_MAX, bool DSM>
 __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* Ab = reinterpret_cast<double*>(smem_raw);  // [NB][Rpad] inner block, column-major per CTA
@@ -121,7 +140,10 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
     int* red_row = red_pos + 2 * PT_WARPS;
     int* pivrow_blk = red_row + 2 * PT_WARPS;  // [NB]
     int* win_sh = pivrow_blk + NB;  // [2][2] winner {pos, row} broadcast by the gathering warp, by column parity
-    unsigned char* s_act = reinterpret_cast<unsigned char*>(win_sh + 4);  // [Rpad] row still active?
+    // cluster variant: cs_hdr[parity][cta][4], cs_row[parity][cta][2 * NB] LL words written by the peers
+    uint2* cs_hdr = reinterpret_cast<uint2*>(win_sh + 4);
+    uint2* cs_row = cs_hdr + 2 * CS_MAX * 4;
+    unsigned char* s_act = reinterpret_cast<unsigned char*>(cs_row + 2 * CS_MAX * 2 * NB);  // [Rpad] row still active?
     int rb = 0;
 
     const int t = threadIdx.x;
@@ -149,6 +171,12 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
         pib[q] = -1;
     }
     for (int lr = t; lr < Rpad; lr += PT_THREADS) s_act[lr] = lr < Rloc ? 1 : 0;
+    if constexpr (DSM) {
+        // no slot may carry a stale epoch: clear them, then let every CTA of the cluster see that before anyone publishes
+        for (int e = t; e < 2 * CS_MAX * (4 + 2 * NB); e += PT_THREADS) cs_hdr[e] = make_uint2(0u, 0u);
+        __syncthreads();
+        cluster_sync_all();
+    }
 
     for (int jb = 0; jb < p.nsteps; jb += NB) {
         const int nbc = min(NB, v - jb);         // columns in this block
@@ -184,6 +212,32 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
         auto publish = [&](const Cand& mine, int jg, int jprev, const double* pw) {
             const unsigned epoch = (unsigned)(p.epoch_base + jg + 1);
             const int par = jg & 1;
+            if constexpr (DSM) {
+                // header + row words into the slot [par][cta] of EVERY CTA of the cluster (remote shared-memory stores)
+                const int words = 4 + 2 * nbc;
+                for (int e = t; e < p.G * words; e += PT_THREADS) {
+                    const int peer = e / words, w = e % words;
+                    unsigned val;
+                    const uint2* slot;
+                    if (w < 4) {
+                        val = w == 0 ? (unsigned)mine.key : w == 1 ? (unsigned)(mine.key >> 32) : w == 2 ? (unsigned)mine.pos : (unsigned)mine.row;
+                        slot = cs_hdr + (size_t)(par * CS_MAX + cta) * 4 + w;
+                    } else {
+                        const int c = (w - 4) >> 1;
+                        double x = 0.0;
+                        if (mine.row >= 0) {
+                            const int lrw = mine.row - row_base;
+                            x = Ab[c * Rpad + lrw];
+                            if (jprev >= 0 && c > jprev + 1) x = fma(-Ab[jprev * Rpad + lrw], pw[c], x);
+                        }
+                        const unsigned long long xb = (unsigned long long)__double_as_longlong(x);
+                        val = ((w - 4) & 1) ? (unsigned)(xb >> 32) : (unsigned)xb;
+                        slot = cs_row + (size_t)(par * CS_MAX + cta) * 2 * NB + (w - 4);
+                    }
+                    st_ll_dsmem(slot, (unsigned)peer, val, epoch);
+                }
+                return;
+            }
             uint2* myhdr = p.slot_hdr + (size_t)(par * MAXG + cta) * 4;
             if (t < 4) {
                 const unsigned w = t == 0 ? (unsigned)mine.key : t == 1 ? (unsigned)(mine.key >> 32)
@@ -251,24 +305,39 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                     // warp 0: one header per lane -> warp-level argmax -> winner (no block barrier)
                     Cand gc{0ull, INT_MAX, -1};
                     if (t < p.G) {
-                        const uint2* h = p.slot_hdr + (size_t)(par * MAXG + t) * 4;
                         uint4 a, b;
-                        do {
-                            a = ld_ll2(h);
-                            b = ld_ll2(h + 2);
-                        } while (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch);
+                        if constexpr (DSM) {
+                            const uint2* h = cs_hdr + (size_t)(par * CS_MAX + t) * 4;   // my own shared memory
+                            do {
+                                a = ld_ll2_smem(h);
+                                b = ld_ll2_smem(h + 2);
+                            } while (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch);
+                        } else {
+                            const uint2* h = p.slot_hdr + (size_t)(par * MAXG + t) * 4;
+                            do {
+                                a = ld_ll2(h);
+                                b = ld_ll2(h + 2);
+                            } while (a.y != epoch || a.w != epoch || b.y != epoch || b.w != epoch);
+                        }
                         gc = Cand{((unsigned long long)a.z << 32) | a.x, (int)b.x, (int)b.z};
                     }
                     TICK(1)
                     const Cand w = warp_argmax(gc);
                     TICK(2)
                     // (w.row < 0 cannot happen while jg < nsteps = min(n, v): some row is still active)
-                    if (!p.spec && t < nbc) {  // dependent fetch of the winner's row only
-                        const uint2* wr = p.slot_rows + (size_t)(par * MAXG + w.row / p.R) * 64 + 2 * t;
+                    if ((DSM || !p.spec) && t < nbc) {  // the winner's row: second L2 round trip, or (cluster) already in my smem
                         uint4 a;
-                        do {
-                            a = ld_ll2(wr);
-                        } while (a.y != epoch || a.w != epoch);
+                        if constexpr (DSM) {
+                            const uint2* wr = cs_row + (size_t)(par * CS_MAX + w.row / p.R) * 2 * NB + 2 * t;
+                            do {
+                                a = ld_ll2_smem(wr);
+                            } while (a.y != epoch || a.w != epoch);
+                        } else {
+                            const uint2* wr = p.slot_rows + (size_t)(par * MAXG + w.row / p.R) * 64 + 2 * t;
+                            do {
+                                a = ld_ll2(wr);
+                            } while (a.y != epoch || a.w != epoch);
+                        }
                         crow[(size_t)par * 32 * NB + (size_t)(w.row / p.R) * NB + t] =
                             __longlong_as_double((long long)(((unsigned long long)a.z << 32) | a.x));
                     }
@@ -276,7 +345,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
                         win_sh[2 * par] = w.pos;
                         win_sh[2 * par + 1] = w.row;
                     }
-                } else if (p.spec) {
+                } else if (!DSM && p.spec) {
                     // warps 1..7: fetch EVERY CTA's candidate row speculatively, all loads of a lane in flight together, so
                     // the winner's row costs no second dependent L2 round trip after the argmax
                     double* cr = crow + (size_t)par * 32 * NB;
@@ -488,32 +557,53 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
         for (int i = p.nsteps + t; i < v; i += PT_THREADS) p.perm_out[i] = i;
     if (cta == 0 && t == 0 && p.dbg != nullptr)
         for (int i = 0; i < 8; ++i) p.dbg[i] = tm[i];
+    if constexpr (DSM) cluster_sync_all();  // nobody may exit while a peer can still store into its shared memory
 #undef TICK
 }
 
 template <int NB>
 size_t panel_smem_bytes(int Rpad, int v) {
     return ((size_t)NB * Rpad + (size_t)NB * v + NB * (NB + 1) + 2 * NB + 2 * 32 * NB) * sizeof(double) +
-           2 * PT_WARPS * (sizeof(unsigned long long) + 2 * sizeof(int)) + (NB + 4) * sizeof(int) + (size_t)Rpad + 64;
+           2 * PT_WARPS * (sizeof(unsigned long long) + 2 * sizeof(int)) + (NB + 4) * sizeof(int) +
+           2 * CS_MAX * (4 + 2 * NB) * sizeof(uint2) + (size_t)Rpad + 64;
 }
 
 template <int NB, int RPT>
-int launch_nb_rpt(PanelArgs& a, cudaStream_t stream) {
+int launch_nb_rpt(PanelArgs& a, bool cluster, cudaStream_t stream) {
     const size_t smem = panel_smem_bytes<NB>(a.Rpad, a.v);
     void* params[] = {&a};
+    if (cluster) {  // the whole grid is ONE thread-block cluster (<= 8 CTAs): DSMEM exchange
+        static PerDeviceMax cfg;
+        if (cfg.raise(smem))
+            CFLX_CUDA(cudaFuncSetAttribute(panel_getrf_kernel<NB, RPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3(a.G);
+        lc.blockDim = dim3(PT_THREADS);
+        lc.dynamicSmemBytes = smem;
+        lc.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = a.G;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        CFLX_CUDA(cudaLaunchKernelExC(&lc, (const void*)panel_getrf_kernel<NB, RPT, true>, params));
+        return CFLX_OK;
+    }
     static PerDeviceMax cfg;
     if (cfg.raise(smem))
-        CFLX_CUDA(cudaFuncSetAttribute(panel_getrf_kernel<NB, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CFLX_CUDA(cudaLaunchCooperativeKernel((void*)panel_getrf_kernel<NB, RPT>, dim3(a.G), dim3(PT_THREADS), params, smem, stream));
+        CFLX_CUDA(cudaFuncSetAttribute(panel_getrf_kernel<NB, RPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CFLX_CUDA(cudaLaunchCooperativeKernel((void*)panel_getrf_kernel<NB, RPT, false>, dim3(a.G), dim3(PT_THREADS), params, smem, stream));
     return CFLX_OK;
 }
 template <int NB>
-int launch_nb(PanelArgs& a, cudaStream_t stream) {
+int launch_nb(PanelArgs& a, bool cluster, cudaStream_t stream) {
     const int rpt = (a.R + PT_THREADS - 1) / PT_THREADS;
-    if (rpt <= 1) return launch_nb_rpt<NB, 1>(a, stream);
-    if (rpt <= 2) return launch_nb_rpt<NB, 2>(a, stream);
-    if (rpt <= 4) return launch_nb_rpt<NB, 4>(a, stream);
-    return launch_nb_rpt<NB, 8>(a, stream);
+    if (rpt <= 1) return launch_nb_rpt<NB, 1>(a, cluster, stream);
+    if (rpt <= 2) return launch_nb_rpt<NB, 2>(a, cluster, stream);
+    if (rpt <= 4) return launch_nb_rpt<NB, 4>(a, cluster, stream);
+    return launch_nb_rpt<NB, 8>(a, cluster, stream);
 }
 }  // namespace
 
@@ -550,6 +640,15 @@ int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, 
     a.n = n;
     a.v = v;
     a.nsteps = n < v ? n : v;
+    // Small panels (tournament stacks, late steps) are latency-bound by the per-column exchange: they run as ONE cluster of
+    // <= 8 CTAs that exchanges candidates through distributed shared memory.  CFLX_CLUSTER_ROWS = largest n handled that
+    // way (0 = never, the default: on B200 the remote-store fan-out measured SLOWER than the L2 exchange, see profiles/).
+    static int cluster_rows = -1;
+    if (cluster_rows < 0) {
+        const char* e = getenv("CFLX_CLUSTER_ROWS");
+        cluster_rows = e ? atoi(e) : 0;  // measured on B200: 2.02 vs 1.58 ms for the 1024 x 512 stack -> off by default
+    }
+    const bool cluster = n > 0 && n <= cluster_rows;
     // as many CTAs as the cap allows down to 32 rows per CTA: small panels (late steps, tournament stacks) are spread
     // over up to 32 SMs and the threads that share a row split the trailing columns in phase C
     int G = (n + 31) / 32;
@@ -561,6 +660,7 @@ int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, 
         const int need = (n + RPT_LIMIT * PT_THREADS - 1) / (RPT_LIMIT * PT_THREADS);
         if (G < need) G = need < ws->max_ctas ? need : ws->max_ctas;
     }
+    if (cluster && G > CS_MAX) G = CS_MAX;
     int R = (n + G - 1) / G;
     R = (int)round_up(R > 0 ? R : 1, 32);
     G = n > 0 ? (n + R - 1) / R : 1;
@@ -599,10 +699,10 @@ int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, 
     }
     if (nb_used) *nb_used = nb;
     switch (nb) {
-        case 32: return launch_nb<32>(a, stream);
-        case 16: return launch_nb<16>(a, stream);
-        case 8: return launch_nb<8>(a, stream);
-        default: return launch_nb<4>(a, stream);
+        case 32: return launch_nb<32>(a, cluster, stream);
+        case 16: return launch_nb<16>(a, cluster, stream);
+        case 8: return launch_nb<8>(a, cluster, stream);
+        default: return launch_nb<4>(a, cluster, stream);
     }
 }
 
