@@ -124,13 +124,30 @@ __global__ void __launch_bounds__(1024) potrf_tile_kernel(double* __restrict__ D
             const int ti = tt / tiles, tj = tt % tiles;
             if (tj > ti) continue;
             const int j = tj * 32 + lane;
-            for (int ii = 0; ii < 32; ++ii) {
-                const int i = ti * 32 + ii;
-                if (i < m && j < m && j <= i) {
-                    double s = 0.0;
+            // 8 rows per iteration: the 8 loads of T are issued together (they are L2 round trips of a single SM), then
+            // the dot products against the shared-memory panel, then the 8 stores
+#pragma unroll 1
+            for (int i0 = 0; i0 < 32; i0 += 8) {
+                double tv[8];
 #pragma unroll
-                    for (int c = 0; c < PB; ++c) s = fma(Xs[i * (PB + 1) + c], Xs[j * (PB + 1) + c], s);
-                    D[(size_t)(jb + nb + i) * v + jb + nb + j] -= s;
+                for (int q = 0; q < 8; ++q) {
+                    const int i = ti * 32 + i0 + q;
+                    tv[q] = (i < m && j < m && j <= i) ? D[(size_t)(jb + nb + i) * v + jb + nb + j] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int i = ti * 32 + i0 + q;
+                    if (i < m && j < m && j <= i) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int c = 0; c < PB; ++c) s = fma(Xs[i * (PB + 1) + c], Xs[j * (PB + 1) + c], s);
+                        tv[q] -= s;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int i = ti * 32 + i0 + q;
+                    if (i < m && j < m && j <= i) D[(size_t)(jb + nb + i) * v + jb + nb + j] = tv[q];
                 }
             }
         }
