@@ -10,8 +10,9 @@ A "step" is one LU factorisation of one synthetic matrix (lu_params::InitMatrix 
     N=4: 32768 x 32768, v=512, grid 2x2x1   (configs[2])
     N=8: 65536 x 65536, v=512, grid 2x2x2   (configs[3])
 `value` times K steps with the matrix already resident in HBM (pristine device copy -> working copy -> factor),
-`e2e` times K steps through the public LU_rep call with the host->device copy of the matrix from pinned memory
-and the device->host read of the permutation inside the timed region.  PyTorch is plumbing only
+`e2e` times K steps through the public LU_rep call with the host->device copy of one matrix per step from pinned
+memory and the device->host read of the permutation inside the timed region (streamed: the upload of the next
+matrix overlaps the current factorisation; `e2e.single_shot` is the un-overlapped latency of one call).  PyTorch is plumbing only
 (torch.distributed bootstrap, pinned host memory).
 """
 import argparse
@@ -86,8 +87,20 @@ def host_mem_bytes():
 _CPU_SNIPPET = r"""
 import os, sys, json
 cores = %(cores)d
-try:                                      # pin the whole process (BLAS pthreads + OpenMP inherit it): stable numbers
-    cpus = sorted(os.sched_getaffinity(0))[:cores]
+def _busy():                              # per-CPU busy jiffies from /proc/stat
+    out = {}
+    for ln in open("/proc/stat"):
+        f = ln.split()
+        if f[0].startswith("cpu") and f[0] != "cpu":
+            t = [int(x) for x in f[1:9]]
+            out[int(f[0][3:])] = (sum(t) - t[3] - t[4], sum(t))
+    return out
+try:                                      # pin the whole process (BLAS pthreads + OpenMP inherit it) to the `cores` CPUs
+    import time                           # that are idle right now: the box is shared, the first CPUs usually are not
+    allowed = sorted(os.sched_getaffinity(0))
+    a = _busy(); time.sleep(0.5); b = _busy()
+    load = {c: (b[c][0] - a[c][0]) / max(1, b[c][1] - a[c][1]) for c in allowed if c in a and c in b}
+    cpus = sorted(sorted(load, key=lambda c: (round(load[c], 1), c))[:cores]) or allowed[:cores]
     os.sched_setaffinity(0, cpus)
 except Exception:
     pass
@@ -109,7 +122,10 @@ def cpu_reference_run(n, v, grid, cores, n_warm, n_rep, budget_s, timeout_s):
     repetitions of the stated configuration, time-boxed.  Returns the child's dict or {"kind": "unavailable: ..."}."""
     P = grid[0] * grid[1] * grid[2]
     thr = max(1, cores // P)
-    env = dict(os.environ, OMP_NUM_THREADS=str(thr), OPENBLAS_NUM_THREADS=str(thr), OMP_PROC_BIND="close")
+    # (no OMP_PROC_BIND: OpenBLAS' pthreads inherit the one-CPU mask of the bound OpenMP thread that creates them -- measured
+    # 13.7 s instead of 0.3 s for N=2048; the process-wide affinity set in the child is what keeps the numbers stable)
+    env = dict(os.environ, OMP_NUM_THREADS=str(thr), OPENBLAS_NUM_THREADS=str(thr))
+    env.pop("OMP_PROC_BIND", None)
     code = _CPU_SNIPPET % dict(root=ROOT, n=n, v=v, grid=tuple(grid), P=P, cores=cores, warm_n=min(n, 8 * v * grid[0]),
                                warm_v=v, n_warm=n_warm, n_rep=n_rep, budget=budget_s)
     try:
@@ -156,6 +172,10 @@ def run_reference_arm(args, rank):
     cores = cpu_threads()
     N, v, grid = WORKLOADS[args.gpus]
     n_s, v_s, g_s, note = reference_plan(args.gpus)
+    if args.N:  # testing only: the line says so
+        N, n_s = args.N, args.N
+        v = v_s = args.v or v
+        note = "size override (testing), not the BASELINE config"
     budget = float(os.environ.get("CFLX_REF_BUDGET_S", "300"))
     t0 = time.time()
     n_warm = 1 if n_s <= 16384 else 0        # big configurations: the small warm-up factorisation only (one rep is minutes)
@@ -174,7 +194,7 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": "LU GFLOP/s (FP64, (2/3)N^3)", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "steps_done": done, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_string(N, v, grid), "generator": GENERATOR, "l2": l2_string(N, v, grid)},
+        "config": {"workload": workload_string(N, v, grid, bool(args.N)), "generator": GENERATOR, "l2": l2_string(N, v, grid)},
         "measured_on": workload_string(n_s, v_s, g_s), "extrapolated": bool(n_s != N),
         "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -410,7 +430,21 @@ def main():
     ms_step = dev_ms / args.steps
     value = flops / (ms_step * 1e-3) / 1e9
 
-    # ---- end-to-end arm: H2D of the matrix + factor + D2H of the permutation, every step -------------------------
+    # ---- end-to-end arm: H2D of one matrix + one factorisation + D2H of the permutation, every step -----------------
+    # (a) streamed: back-to-back factorisations with double-buffered input -- every step uploads one full matrix from
+    # pinned host memory on a copy stream (the input of the NEXT step, cflx_lu_queue_next_local), factors the matrix
+    # the previous step uploaded, and reads its permutation back: K uploads, K factorisations, K read-backs per K steps
+    cb.LU_rep(gv, None, perm, upload=True, next_data=gv.data)
+    cb.LU_rep(gv, None, perm, upload=False, next_data=gv.data)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cb.LU_rep(gv, None, perm, upload=False, next_data=gv.data)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    e2e_val = flops / (e2e_ms * 1e-3) / 1e9
+    # (b) single shot: upload, then factor, then read back, nothing overlapped (the latency of ONE call; step 0 of a
+    # factorisation touches the whole matrix, so the transfer cannot hide inside a single run -- DESIGN.md section 5)
     for _ in range(2):
         cb.LU_rep(gv, None, perm, upload=True)
     barrier()
@@ -418,8 +452,8 @@ def main():
     for _ in range(args.steps):
         cb.LU_rep(gv, None, perm, upload=True)
     barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
-    e2e_val = flops / (e2e_ms * 1e-3) / 1e9
+    e2e1_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    e2e1_val = flops / (e2e1_ms * 1e-3) / 1e9
 
     # ---- parity of the run that was just timed (every rank takes part: the residual is a grid collective) ------------
     ok_perm = sorted(perm.tolist()) == list(range(gv.M))
@@ -447,7 +481,11 @@ def main():
             "timing": "CUDA events on the launching stream around each factorisation's main loop, max over ranks",
             "wall_ms_per_step_incl_restore_copy": wall_ms / args.steps,
             "e2e": {"value": e2e_val, "unit": "GFLOP/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(gv.Ml * gv.Nl * 8),
-                    "d2h_bytes_per_step": int(gv.M * 4)},
+                    "d2h_bytes_per_step": int(gv.M * 4),
+                    "mode": "streamed: every step uploads one matrix (pinned host -> HBM, copy stream) while the matrix uploaded "
+                            "by the previous step is factored, then reads the permutation back (public LU_rep(next_data=...))",
+                    "single_shot": {"value": e2e1_val, "ms_per_step": e2e1_ms,
+                                    "mode": "upload, factor, read back in sequence: the latency of one isolated call"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor",
@@ -481,6 +519,9 @@ def main():
             cores = cpu_threads()
             n_s = 8192
             d = cpu_reference_run(n_s, 256, (1, 1, 1), cores, 1, 2, 40.0, timeout_s=240)
+            if not d.get("inner_ms"):      # a crowded host: a sample 8x smaller rather than no number at all
+                n_s = 4096
+                d = cpu_reference_run(n_s, 256, (1, 1, 1), cores, 1, 2, 20.0, timeout_s=180)
             ms = min(d["inner_ms"]) if d.get("inner_ms") else None
             line["cpu_baseline"] = {"value": ((2.0 / 3.0) * n_s ** 3 / (ms * 1e-3) / 1e9) if ms else None, "unit": "GFLOP/s",
                                     "cores": cores, "kind": d.get("kind"),

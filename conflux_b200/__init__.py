@@ -151,13 +151,20 @@ class lu_params:
             pass
 
 
-def LU_rep(gv, C=None, permutation=None, upload=True):
+def LU_rep(gv, C=None, permutation=None, upload=True, next_data=None):
     """conflux::LU_rep<double>(gv, C, permutation) (conflux_opt.hpp:343-346): collective over gv.lu_comm, does not
     modify gv.data, fills C (Ml x Nl, L\\U of PA in the conflux layout, layer 0) and permutation (M ints) when they
-    are given, returns the time of the main loop in ms (device-timed)."""
+    are given, returns the time of the main loop in ms (device-timed).
+
+    upload=True copies gv.data to the device first; upload=False factors the input that is already there (the previous
+    one, or the matrix a previous call streamed in through next_data).  next_data (page-locked array of gv.data's shape):
+    the input of the NEXT factorisation, uploaded on a copy stream while this one runs (cflx_lu_queue_next_local)."""
     if upload:
         a = np.ascontiguousarray(gv.data, dtype=np.float64)
         check(lib().cflx_lu_set_local(gv._h, a.ctypes.data), "lu_set_local")
+    if next_data is not None:
+        assert next_data.dtype == np.float64 and next_data.flags.c_contiguous and next_data.size == gv.Ml * gv.Nl
+        check(lib().cflx_lu_queue_next_local(gv._h, next_data.ctypes.data), "lu_queue_next_local")
     ms = ctypes.c_double()
     check(lib().cflx_lu_factor(gv._h, ctypes.byref(ms)), "lu_factor")
     if C is not None:

@@ -21,7 +21,7 @@ class ConfluxError(RuntimeError):
 SYMBOLS = [
     "cflx_last_error", "cflx_version", "cflx_device_count", "cflx_get_unique_id", "cflx_comm_create",
     "cflx_comm_barrier", "cflx_comm_destroy", "cflx_host_alloc", "cflx_host_free", "cflx_auto_grid", "cflx_lu_dims", "cflx_init_matrix_host",
-    "cflx_lu_create", "cflx_lu_info", "cflx_lu_set_local", "cflx_lu_factor", "cflx_lu_get_factors",
+    "cflx_lu_create", "cflx_lu_info", "cflx_lu_set_local", "cflx_lu_queue_next_local", "cflx_lu_factor", "cflx_lu_get_factors",
     "cflx_lu_get_permutation", "cflx_lu_residual", "cflx_lu_validate", "cflx_lu_launch_count", "cflx_lu_uses_tcgen05", "cflx_lu_set_profiling", "cflx_lu_phase_ms", "cflx_lu_timeline",
     "cflx_lu_set_kernel_timing", "cflx_lu_trailing_stats", "cflx_lu_destroy", "cflx_chol_auto_grid", "cflx_chol_auto_tile", "cflx_chol_dims", "cflx_chol_init_matrix_host",
     "cflx_chol_create", "cflx_chol_info", "cflx_chol_set_local", "cflx_chol_factor", "cflx_chol_get_local", "cflx_chol_validate",
@@ -68,6 +68,7 @@ def lib():
         L.cflx_host_free.argtypes = [ctypes.c_void_p]
         L.cflx_lu_info.argtypes = [ctypes.c_void_p, c_int_p]
         L.cflx_lu_set_local.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.cflx_lu_queue_next_local.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.cflx_lu_factor.argtypes = [ctypes.c_void_p, c_double_p]
         L.cflx_lu_get_factors.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.cflx_lu_get_permutation.argtypes = [ctypes.c_void_p, ctypes.c_void_p]

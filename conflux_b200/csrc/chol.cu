@@ -32,7 +32,7 @@ struct cflx_chol {
     int pi = 0, pj = 0, pk = 0, rank = 0;
     SubComm k_comm, i_comm;
     double *A0 = nullptr, *A11 = nullptr, *PT = nullptr, *LT = nullptr, *G = nullptr /* [2] */, *Bc = nullptr /* [2] */, *D = nullptr, *A00 = nullptr,
-           *W = nullptr, *Uinv = nullptr, *LinvT = nullptr, *acc = nullptr;
+           *W = nullptr, *Uinv = nullptr, *LinvT = nullptr, *acc = nullptr, *Q = nullptr /* scratch of the blocked tile Cholesky */;
     int* info = nullptr;
     int64_t ldp = 0, ldb = 0;
     OzakiWorkspace oz{};                    // digit planes of the int8 tcgen05 rank-v update (default when v / Pz is 128..512)
@@ -51,7 +51,10 @@ namespace {
 //   UT  out: L^T (upper triangular, row-major) -- the operand of the panel TRSM and what is broadcast
 // info[0] = 1 + index of the first non-positive pivot (0 = success), like LAPACK's dpotrf.
 constexpr int PB = 32;
-__global__ void __launch_bounds__(1024) potrf_tile_kernel(double* __restrict__ D, int v, double* __restrict__ UT, int* __restrict__ info) {
+// D: v x v window (leading dimension ldd) of the tile, UT: the same window of L^T (leading dimension ldu); Uc (optional): a
+// contiguous v x v copy of the factored block's L^T; col_off: column of the window inside the whole tile (for *info)
+__global__ void __launch_bounds__(1024) potrf_tile_kernel(double* __restrict__ D, int v, int ldd, double* __restrict__ UT, int ldu,
+                                                          double* __restrict__ Uc, int* __restrict__ info, int col_off) {
     extern __shared__ double sm[];
     double* Ld = sm;                 // [PB][PB + 1] factored diagonal block
     double* Xs = sm + PB * (PB + 1);  // [v][PB + 1] panel below it
@@ -60,7 +63,7 @@ __global__ void __launch_bounds__(1024) potrf_tile_kernel(double* __restrict__ D
     if (t == 0) s_bad = 0;
     for (int jb = 0; jb < v; jb += PB) {
         const int nb = min(PB, v - jb), m = v - jb - nb;
-        for (int e = t; e < nb * nb; e += blockDim.x) Ld[(e / nb) * (PB + 1) + e % nb] = D[(size_t)(jb + e / nb) * v + jb + e % nb];
+        for (int e = t; e < nb * nb; e += blockDim.x) Ld[(e / nb) * (PB + 1) + e % nb] = D[(size_t)(jb + e / nb) * ldd + jb + e % nb];
         __syncthreads();
         if (warp == 0) {  // lane = row of the block, the row lives in registers
             double a[PB];
@@ -70,7 +73,7 @@ __global__ void __launch_bounds__(1024) potrf_tile_kernel(double* __restrict__ D
             for (int c = 0; c < PB; ++c) {
                 if (c < nb) {
                     const double d = __shfl_sync(0xffffffffu, a[c], c);
-                    if (!(d > 0.0) && lane == 0 && s_bad == 0) s_bad = jb + c + 1;
+                    if (!(d > 0.0) && lane == 0 && s_bad == 0) s_bad = col_off + jb + c + 1;
                     const double sq = sqrt(d);
                     if (lane == c) a[c] = sq;
                     else if (lane > c) a[c] = a[c] / sq;
@@ -90,12 +93,12 @@ __global__ void __launch_bounds__(1024) potrf_tile_kernel(double* __restrict__ D
         for (int e = t; e < nb * nb; e += blockDim.x) {
             const int r = e / nb, c = e % nb;
             const double x = Ld[r * (PB + 1) + c];
-            D[(size_t)(jb + r) * v + jb + c] = x;
-            UT[(size_t)(jb + c) * v + jb + r] = x;          // UT[c][r] = L[r][c] (zero for c > r)
+            D[(size_t)(jb + r) * ldd + jb + c] = x;
+            UT[(size_t)(jb + c) * ldu + jb + r] = x;          // UT[c][r] = L[r][c] (zero for c > r)
         }
         // panel below: X = P * L_d^-T, one thread per row (forward substitution against the block in shared memory)
         for (int i = t; i < m; i += blockDim.x) {
-            double* prow = D + (size_t)(jb + nb + i) * v + jb;
+            double* prow = D + (size_t)(jb + nb + i) * ldd + jb;
             double x[PB];
 #pragma unroll
             for (int c = 0; c < PB; ++c) x[c] = c < nb ? prow[c] : 0.0;
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(1024) potrf_tile_kernel(double* __restrict__ D
                 if (c < nb) {
                     prow[c] = x[c];
                     Xs[i * (PB + 1) + c] = x[c];
-                    UT[(size_t)(jb + c) * v + jb + nb + i] = x[c];   // L^T
+                    UT[(size_t)(jb + c) * ldu + jb + nb + i] = x[c];   // L^T
                 }
             }
         }
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(1024) potrf_tile_kernel(double* __restrict__ D
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const int i = ti * 32 + i0 + q;
-                    tv[q] = (i < m && j < m && j <= i) ? D[(size_t)(jb + nb + i) * v + jb + nb + j] : 0.0;
+                    tv[q] = (i < m && j < m && j <= i) ? D[(size_t)(jb + nb + i) * ldd + jb + nb + j] : 0.0;
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(1024) potrf_tile_kernel(double* __restrict__ D
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const int i = ti * 32 + i0 + q;
-                    if (i < m && j < m && j <= i) D[(size_t)(jb + nb + i) * v + jb + nb + j] = tv[q];
+                    if (i < m && j < m && j <= i) D[(size_t)(jb + nb + i) * ldd + jb + nb + j] = tv[q];
                 }
             }
         }
@@ -157,11 +160,26 @@ __global__ void __launch_bounds__(1024) potrf_tile_kernel(double* __restrict__ D
     for (int e = t; e < v * v; e += blockDim.x) {
         const int r = e / v, c = e % v;
         if (c > r) {
-            D[e] = 0.0;
-            UT[(size_t)c * v + r] = 0.0;
+            D[(size_t)r * ldd + c] = 0.0;
+            UT[(size_t)c * ldu + r] = 0.0;
         }
     }
+    if (Uc != nullptr) {
+        __syncthreads();
+        for (int e = t; e < v * v; e += blockDim.x) Uc[e] = UT[(size_t)(e / v) * ldu + e % v];
+    }
     if (t == 0 && s_bad) info[0] = s_bad;
+}
+
+// zeros above the diagonal of D (= L) and below the diagonal of UT (= L^T)
+__global__ void tri_clean_kernel(double* __restrict__ D, double* __restrict__ UT, int v) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= v * v) return;
+    const int r = e / v, c = e % v;
+    if (c > r) {
+        D[e] = 0.0;
+        UT[(size_t)c * v + r] = 0.0;
+    }
 }
 
 // D[r][c] = PT[c][r] (diagonal tile out of the transposed panel) / A11 tile <- D
@@ -248,7 +266,7 @@ int chol_pick_nb(int v) {
 void free_chol(cflx_chol* ch) {
     if (!ch) return;
     cudaSetDevice(ch->comm->device);
-    for (double* p : {ch->A0, ch->A11, ch->PT, ch->LT, ch->W, ch->G, ch->Bc, ch->D, ch->A00, ch->Uinv, ch->LinvT, ch->acc}) cudaFree(p);
+    for (double* p : {ch->A0, ch->A11, ch->PT, ch->LT, ch->W, ch->G, ch->Bc, ch->D, ch->A00, ch->Uinv, ch->LinvT, ch->acc, ch->Q}) cudaFree(p);
     cudaFree(ch->info);
     if (ch->use_ozaki) ozaki_workspace_destroy(&ch->oz);
     if (ch->side) cudaStreamDestroy(ch->side);
@@ -368,6 +386,54 @@ int broadcast_and_update(cflx_chol* ch, int t, int jmin, bool below_only, double
 
 // Panel pipeline of step k on stream s: z-reduce of tile column k, Cholesky of the diagonal tile, L_kk^T down the grid
 // column, the panel solve, the stores, and (k < Kappa - 1) the broadcast of the panel pieces into buffer set k & 1.
+// (1) Cholesky of the v x v diagonal tile.  One CTA needs 2.2 ms for a 512 x 512 tile (measured: 2/3 of a whole 16384^2
+// factorisation), so the tile is itself factored in 128-wide block columns: the 128 x 128 diagonal block on one CTA, the
+// block column below it by ONE GEMM with the inverted block, the trailing part of the tile by one rank-128 GEMM -- both on
+// the whole GPU (FP64 DMMA kernel).  Tiles that are not a multiple of 128 (tests) keep the one-CTA kernel.
+int potrf_tile(cflx_chol* ch, size_t psm, cudaStream_t s) {
+    const int v = ch->v;
+    constexpr int QB = 128;
+    if (v % QB != 0 || v < 2 * QB || ch->Q == nullptr) {
+        potrf_tile_kernel<<<1, 1024, psm, s>>>(ch->D, v, v, ch->A00, v, nullptr, ch->info + 1, 0);
+        CFLX_CUDA(cudaGetLastError());
+        return CFLX_OK;
+    }
+    double* U128 = ch->Q;                      // [QB][QB]  L_d^T of the current diagonal block, contiguous
+    double* Ui = U128 + QB * QB;               // [QB][QB]  its inverse
+    double* Li = Ui + QB * QB;                 // [QB][QB]  (unit-lower companion of launch_diag_inverses, unused)
+    double* XT0 = Li + QB * QB;                // [QB][v]   block column below the diagonal block, transposed
+    double* XT = XT0 + (size_t)QB * v;         // [QB][v]   ... after the solve
+    const size_t psm_q = ((size_t)PB * (PB + 1) + (size_t)QB * (PB + 1)) * sizeof(double);
+    for (int jb = 0; jb < v; jb += QB) {
+        const int m = v - jb - QB;
+        potrf_tile_kernel<<<1, 1024, psm_q, s>>>(ch->D + (size_t)jb * v + jb, QB, v, ch->A00 + (size_t)jb * v + jb, v, U128,
+                                                 ch->info + 1, jb);
+        CFLX_CUDA(cudaGetLastError());
+        ch->launches++;
+        if (m <= 0) break;
+        const int64_t ldx = m;
+        CFLX_TRY(launch_extract_panel_T(ch->D, v, jb + QB, jb, m, QB, XT0, ldx, s));
+        CFLX_TRY(launch_diag_inverses(U128, QB, QB, Ui, Li, s));
+        CFLX_TRY(trsm_right_upper_T(U128, Ui, QB, QB, XT0, XT, ldx, m, s));          // X^T = L_d^-1 P^T
+        CFLX_TRY(launch_store_panel_T(ch->D, v, jb + QB, jb, m, QB, XT, ldx, s));
+        CFLX_CUDA(cudaMemcpy2DAsync(ch->A00 + (size_t)jb * v + jb + QB, (size_t)v * sizeof(double), XT, ldx * sizeof(double),
+                                    (size_t)m * sizeof(double), QB, cudaMemcpyDeviceToDevice, s));
+        GemmArgs g{};                                                                 // T -= X X^T
+        g.M = m; g.N = m; g.K = QB;
+        g.AT = XT; g.ldat = ldx;
+        g.B = XT; g.ldb = ldx;
+        g.C = ch->D + (size_t)(jb + QB) * v + jb + QB; g.ldc = v;
+        g.D = ch->D + (size_t)(jb + QB) * v + jb + QB; g.ldd = v;
+        g.alpha = -1.0; g.beta = 1.0;
+        CFLX_TRY(launch_gemm_tn(g, s));
+        ch->launches += 6;
+    }
+    tri_clean_kernel<<<(v * v + 255) / 256, 256, 0, s>>>(ch->D, ch->A00, v);
+    CFLX_CUDA(cudaGetLastError());
+    ch->launches++;
+    return CFLX_OK;
+}
+
 int panel_step(cflx_chol* ch, int k, cudaStream_t s) {
     const int v = ch->v, Px = ch->Px, Py = ch->Py, Pz = ch->Pz, Ml = ch->Ml, Nl = ch->Nl;
     const int pi = ch->pi, pj = ch->pj, pk = ch->pk;
@@ -390,7 +456,7 @@ int panel_step(cflx_chol* ch, int k, cudaStream_t s) {
     // (1) Cholesky of the diagonal tile                                                 Cholesky.cpp:188-193
     if (owner) {
         tile_from_panel_kernel<<<(v * v + 255) / 256, 256, 0, s>>>(ch->PT, ld, v, ch->D);
-        potrf_tile_kernel<<<1, 1024, psm, s>>>(ch->D, v, ch->A00, ch->info + 1);
+        CFLX_TRY(potrf_tile(ch, psm, s));
         tile_store_kernel<<<(v * v + 255) / 256, 256, 0, s>>>(ch->D, v, ch->A11 + (int64_t)row0 * Nl + loff, Nl);
         CFLX_CUDA(cudaGetLastError());
         ch->launches += 3;
@@ -533,6 +599,7 @@ int cflx_chol_create(cflx_comm* c, int N, int v, int Px, int Py, int Pz, cflx_ch
     ALLOC(ch->G, 2 * (size_t)Px * v * ch->ldp); ALLOC(ch->Bc, 2 * (size_t)v * ch->ldb);
     ALLOC(ch->D, vv); ALLOC(ch->A00, vv); ALLOC(ch->Uinv, vv); ALLOC(ch->LinvT, vv); ALLOC(ch->acc, 4);
     ALLOC(ch->info, 4);
+    if (v % 128 == 0 && v >= 256) ALLOC(ch->Q, (size_t)3 * 128 * 128 + (size_t)2 * 128 * v);
 #undef ALLOC
     cudaMemsetAsync(ch->PT, 0, (size_t)v * ch->ldp * sizeof(double), c->stream);
     cudaMemsetAsync(ch->LT, 0, (size_t)v * ch->ldp * sizeof(double), c->stream);

@@ -54,6 +54,12 @@ struct PanelWorkspace {
     int epoch;          // host-side running epoch (monotonic across launches)
     int max_ctas;       // co-resident CTA budget (<= 148)
     int cta_cap;        // optional cap on the grid (look-ahead: leave SMs to the trailing update); 0 = none
+    // column-owner kernel for panels of <= 1024 rows (tournament stacks)
+    unsigned* sk_flags;  // [1024] epoch of the last publication of column block b
+    int* sk_ppos;        // [v] LAPACK position of every pivot when it was chosen
+    unsigned* sk_ticket; // logical CTA ids in start order
+    unsigned sk_epoch, sk_ticket_count;
+    int sk_enabled;
 };
 int panel_workspace_create(PanelWorkspace* ws);
 void panel_workspace_destroy(PanelWorkspace* ws);

@@ -511,6 +511,9 @@ void free_lu(cflx_lu* lu) {
     if (lu->ev_fork) cudaEventDestroy(lu->ev_fork);
     if (lu->ev_join) cudaEventDestroy(lu->ev_join);
     if (lu->ev_npiv) cudaEventDestroy(lu->ev_npiv);
+    if (lu->copy) cudaStreamDestroy(lu->copy);
+    if (lu->ev_a0_read) cudaEventDestroy(lu->ev_a0_read);
+    if (lu->ev_upload) cudaEventDestroy(lu->ev_upload);
     for (SubComm* sc : {&lu->k_comm, &lu->i_comm, &lu->jk_comm, &lu->ik_comm})
         if (sc->c) ncclCommDestroy(sc->c);
     delete lu;
@@ -785,6 +788,28 @@ int cflx_lu_set_local(cflx_lu* lu, const double* host_local) {
     CFLX_CUDA(cudaStreamSynchronize(lu->comm->stream));
     lu->have_input = true;
     lu->factored = false;
+    lu->a0_is_next = false;
+    lu->next_host = nullptr;
+    return CFLX_OK;
+}
+
+// Input streaming for back-to-back factorisations: the NEXT cflx_lu_factor call uploads `host_next` (page-locked memory,
+// valid until that call returns) into the input buffer on a copy stream as soon as it has taken its own working copy of
+// the current input, so the 8*Ml*Nl-byte transfer overlaps the factorisation; the factorisation after that consumes it
+// without a cflx_lu_set_local.  The residual of a run whose input buffer was handed to the next matrix is refused.
+int cflx_lu_queue_next_local(cflx_lu* lu, const double* host_next) {
+    if (!lu || !host_next) return CFLX_ERR_ARG;
+    if (!lu->have_input) {
+        set_last_error("cflx_lu_queue_next_local needs a current input (cflx_lu_set_local) first");
+        return CFLX_ERR_STATE;
+    }
+    CFLX_CUDA(cudaSetDevice(lu->comm->device));
+    if (!lu->copy) {
+        CFLX_CUDA(cudaStreamCreateWithFlags(&lu->copy, cudaStreamNonBlocking));
+        CFLX_CUDA(cudaEventCreateWithFlags(&lu->ev_a0_read, cudaEventDisableTiming));
+        CFLX_CUDA(cudaEventCreateWithFlags(&lu->ev_upload, cudaEventDisableTiming));
+    }
+    lu->next_host = host_next;
     return CFLX_OK;
 }
 
@@ -801,7 +826,17 @@ int cflx_lu_factor(cflx_lu* lu, double* ms_out) {
     // "init" region of the reference (conflux_opt.hpp:347-515): A11Buff = copy of gv.data, gri, counters
     {
         PhaseTimer t(lu, RG_init, s);
+        if (lu->a0_is_next) CFLX_CUDA(cudaStreamWaitEvent(s, lu->ev_upload, 0));  // this run's input was streamed in
         CFLX_CUDA(cudaMemcpyAsync(lu->A11, lu->A0, loc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    }
+    lu->a0_is_next = false;
+    if (lu->next_host) {  // queued next input: overwrite A0 behind the working copy, concurrently with everything below
+        CFLX_CUDA(cudaEventRecord(lu->ev_a0_read, s));
+        CFLX_CUDA(cudaStreamWaitEvent(lu->copy, lu->ev_a0_read, 0));
+        CFLX_CUDA(cudaMemcpyAsync(lu->A0, lu->next_host, loc * sizeof(double), cudaMemcpyHostToDevice, lu->copy));
+        CFLX_CUDA(cudaEventRecord(lu->ev_upload, lu->copy));
+        lu->next_host = nullptr;
+        lu->a0_is_next = true;
     }
     CFLX_TRY(launch_iota_gri(lu->gri, lu->igri, lu->Ml, lu->v, lu->Px, lu->pi, s));
     for (double& x : lu->phase_ms) x = 0;
@@ -872,6 +907,7 @@ int cflx_lu_factor(cflx_lu* lu, double* ms_out) {
             else cudaGetLastError();
         }
     }
+    if (lu->a0_is_next) CFLX_CUDA(cudaStreamSynchronize(lu->copy));  // the caller's staging buffer is free again
     lu->factored = true;
     return CFLX_OK;
 }
@@ -919,6 +955,10 @@ int cflx_lu_validate(cflx_lu* lu, double* frob_abs_out, double* frob_rel_out) {
     if (!lu) return CFLX_ERR_ARG;
     if (!lu->factored) {
         set_last_error("residual requested before cflx_lu_factor");
+        return CFLX_ERR_STATE;
+    }
+    if (lu->a0_is_next) {
+        set_last_error("residual refused: the input buffer of the last run was handed to the queued next matrix");
         return CFLX_ERR_STATE;
     }
     CFLX_CUDA(cudaSetDevice(lu->comm->device));

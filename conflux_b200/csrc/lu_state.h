@@ -82,6 +82,11 @@ struct cflx_lu {
     int* h_npiv = nullptr;  // pinned
     std::vector<int> h_hist;
     bool have_input = false, factored = false, time_gemm = false;
+    // double-buffered input streaming (cflx_lu_queue_next_local): the upload of the NEXT matrix overlaps this factorisation
+    const double* next_host = nullptr;
+    bool a0_is_next = false;  // A0 already holds (or is receiving) the next input: validation of the last run is refused
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev_a0_read = nullptr, ev_upload = nullptr;
     double gemm_ms = 0, gemm_flops = 0;
     int64_t launches = 0;
     double phase_ms[cflx::PH_COUNT] = {0};

@@ -561,6 +561,200 @@ __global__ void __launch_bounds__(PT_THREADS, 1) panel_getrf_kernel(PanelArgs p)
 #undef TICK
 }
 
+// =====================================================================================================================
+// Small panels (n <= 1024 rows: the 2v x v stacks of the tournament rounds, conflux_opt.hpp:291, and the last local
+// panels): COLUMN-block owners instead of row owners.  A 1024-row column block of 16 columns fits the registers of one
+// CTA (one row per thread), so the pivot search over such a block needs NO exchange between CTAs at all: two block
+// barriers per column instead of an L2 round trip.  CTA c owns columns [16c, 16c+16): it applies the published blocks
+// b < c to its columns (right-looking, U12 by forward substitution with the publisher's L11, then the rank-16 update from
+// registers), factors its own block, writes it back in place and raises flag c.  The chain that matters is
+// publish(b) -> update + factor in CTA b+1 -> publish(b+1); every other CTA trails behind it.  Logical CTA ids are handed
+// out by an atomic ticket, so a CTA only ever waits for CTAs that started before it (no co-residency requirement).
+// Arithmetic = the same fma chain per element, in the same order, as panel_getrf_kernel: results are bit-identical.
+constexpr int SK_CB = 16;
+struct StackArgs {
+    double* W;
+    int64_t ldw;
+    int n, v;
+    int* perm_out;      // [v]
+    int* ppos;          // [v] LAPACK position of pivot j at the time it was chosen (replays the interchanges)
+    unsigned* flags;    // [v / SK_CB] == epoch once the block is published
+    unsigned* ticket;
+    unsigned ticket_base, epoch;
+};
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) stack_getrf_kernel(StackArgs p) {
+    __shared__ double A12s[SK_CB][SK_CB + 1];  // pivot rows of block b in my columns, then U12
+    __shared__ double L11s[SK_CB][SK_CB + 1];  // their multipliers inside block b
+    __shared__ double prow[2][SK_CB];
+    __shared__ unsigned long long red_key[2][32];
+    __shared__ int red_pos[2][32], red_row[2][32];
+    __shared__ int pivs[SK_CB], ppos_s[SK_CB];
+    __shared__ int s_cta;
+    extern __shared__ __align__(16) double Ls[];  // [SK_CB][NT] multipliers of the block being applied, row t in column t
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31, nw = blockDim.x >> 5;
+    if (t == 0) s_cta = (int)(atomicAdd(p.ticket, 1u) - p.ticket_base);
+    __syncthreads();
+    const int c = s_cta, c0 = c * SK_CB;
+    const bool valid = t < p.n;
+    double* __restrict__ W = p.W;
+    const int64_t ldw = p.ldw;
+    double a[SK_CB];
+#pragma unroll
+    for (int j = 0; j < SK_CB; ++j) a[j] = valid ? W[(int64_t)(c0 + j) * ldw + t] : 0.0;
+    int pos = t;     // LAPACK position of my row (rows never move)
+    int mypiv = -1;  // global pivot index once my row has been chosen
+
+    for (int b = 0; b < c; ++b) {
+        if (t == 0)
+            while (ld_acquire_u32(p.flags + b) != p.epoch) {}
+        __syncthreads();  // block b is published (and nobody still reads the shared tiles of the previous block)
+        if (t < SK_CB) {
+            pivs[t] = ld_cg_s32(p.perm_out + b * SK_CB + t);
+            ppos_s[t] = ld_cg_s32(p.ppos + b * SK_CB + t);
+        }
+        // the multipliers of block b (n x 16) go straight into shared memory with 16-byte asynchronous copies (.cg: L2 only --
+        // a stale L1 line must never serve data another CTA published); no registers are held while the round trip is in
+        // flight and it overlaps the forward substitution below.  Thread (h, q) copies rows 2q, 2q+1 of columns 8h..8h+7.
+        {
+            const int half = blockDim.x >> 1, q = t % half, h = t / half;
+            if (2 * q < p.n) {
+                const double* lp = W + (int64_t)(b * SK_CB + 8 * h) * ldw + 2 * q;
+#pragma unroll
+                for (int k = 0; k < SK_CB / 2; ++k) cp_async16(Ls + (8 * h + k) * NT + 2 * q, lp + (int64_t)k * ldw);
+            }
+        }
+        cp_async_commit();
+        __syncthreads();
+        int kk = -1;
+        if (mypiv < 0) {
+#pragma unroll
+            for (int k = 0; k < SK_CB; ++k) {
+                if (pivs[k] == t) kk = k;
+                else if (kk < 0 && pos == b * SK_CB + k) pos = ppos_s[k];  // my row is swapped into the winner's old place
+            }
+        }
+        if (kk >= 0) {
+#pragma unroll
+            for (int j = 0; j < SK_CB; ++j) A12s[kk][j] = a[j];
+#pragma unroll
+            for (int k = 0; k < SK_CB; ++k) L11s[kk][k] = ld_cg_f64(W + (int64_t)(b * SK_CB + k) * ldw + t);
+        }
+        __syncthreads();
+        if (t < SK_CB) {  // U12 = L11^-1 A12 in place, one column per thread, the same fma chain as phase C of panel_getrf_kernel
+#pragma unroll
+            for (int i = 1; i < SK_CB; ++i) {
+                double x = A12s[i][t];
+#pragma unroll
+                for (int s2 = 0; s2 < i; ++s2) x = fma(-L11s[i][s2], A12s[s2][t], x);
+                A12s[i][t] = x;
+            }
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        if (kk >= 0) {  // my row is pivot kk of block b: it keeps its U values
+#pragma unroll
+            for (int j = 0; j < SK_CB; ++j) a[j] = A12s[kk][j];
+            mypiv = b * SK_CB + kk;
+        } else if (mypiv < 0 && valid) {
+#pragma unroll
+            for (int k = 0; k < SK_CB; ++k) {
+                const double lk = Ls[k * NT + t];
+#pragma unroll
+                for (int j = 0; j < SK_CB; ++j) a[j] = fma(-lk, A12s[k][j], a[j]);
+            }
+        }
+    }
+
+    // ---- my own block: partial pivoting entirely inside the CTA ----
+#pragma unroll
+    for (int j = 0; j < SK_CB; ++j) {
+        const int jg = c0 + j, par = j & 1;
+        Cand cd{0ull, INT_MAX, -1};
+        if (valid && mypiv < 0) cd = Cand{(unsigned long long)__double_as_longlong(fabs(a[j])), pos, t};
+        const Cand w1 = warp_argmax(cd);
+        if (lane == 0) {
+            red_key[par][warp] = w1.key;
+            red_pos[par][warp] = w1.pos;
+            red_row[par][warp] = w1.row;
+        }
+        __syncthreads();
+        Cand x{0ull, INT_MAX, -1};
+        if (lane < nw) x = Cand{red_key[par][lane], red_pos[par][lane], red_row[par][lane]};
+        const Cand win = warp_argmax(x);  // identical in every warp
+        if (t == win.row) {
+#pragma unroll
+            for (int m = 0; m < SK_CB; ++m) prow[par][m] = a[m];
+            mypiv = jg;
+        }
+        if (t == 0) {
+            p.perm_out[jg] = win.row;
+            p.ppos[jg] = win.pos;
+        }
+        __syncthreads();
+        if (valid && mypiv < 0) {
+            if (pos == jg) pos = win.pos;
+            const double pivot = prow[par][j];
+            const double rinv = pivot != 0.0 ? 1.0 / pivot : 0.0;
+            double lq = 0.0;
+            if (pivot != 0.0) {
+                lq = a[j] * rinv;
+                a[j] = lq;
+            }
+#pragma unroll
+            for (int m = j + 1; m < SK_CB; ++m) a[m] = fma(-lq, prow[par][m], a[m]);
+        }
+    }
+    if (valid) {
+#pragma unroll
+        for (int j = 0; j < SK_CB; ++j) W[(int64_t)(c0 + j) * ldw + t] = a[j];
+    }
+    __threadfence();
+    __syncthreads();
+    if (t == 0) st_release_u32(p.flags + c, p.epoch);
+}
+
+int launch_stack_getrf(double* W, int64_t ldw, int n, int v, int* perm_out, PanelWorkspace* ws, cudaStream_t stream) {
+    StackArgs a{};
+    a.W = W;
+    a.ldw = ldw;
+    a.n = n;
+    a.v = v;
+    a.perm_out = perm_out;
+    a.ppos = ws->sk_ppos;
+    a.flags = ws->sk_flags;
+    a.ticket = ws->sk_ticket;
+    a.ticket_base = ws->sk_ticket_count;
+    a.epoch = ++ws->sk_epoch;
+    const int C = v / SK_CB;
+    ws->sk_ticket_count += (unsigned)C;
+    const int threads = (int)round_up(n, 32);
+    static PerDeviceMax cfg;
+    if (cfg.raise((size_t)SK_CB * 1024 * sizeof(double))) {
+        CFLX_CUDA(cudaFuncSetAttribute(stack_getrf_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_CB * 1024 * 8));
+        CFLX_CUDA(cudaFuncSetAttribute(stack_getrf_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_CB * 512 * 8));
+    }
+    if (threads <= 256) stack_getrf_kernel<256><<<C, threads, SK_CB * 256 * sizeof(double), stream>>>(a);
+    else if (threads <= 512) stack_getrf_kernel<512><<<C, threads, SK_CB * 512 * sizeof(double), stream>>>(a);
+    else stack_getrf_kernel<1024><<<C, threads, SK_CB * 1024 * sizeof(double), stream>>>(a);
+    CFLX_CUDA(cudaGetLastError());
+    return CFLX_OK;
+}
+
 template <int NB>
 size_t panel_smem_bytes(int Rpad, int v) {
     return ((size_t)NB * Rpad + (size_t)NB * v + NB * (NB + 1) + 2 * NB + 2 * 32 * NB) * sizeof(double) +
@@ -620,12 +814,27 @@ int panel_workspace_create(PanelWorkspace* ws) {
     CFLX_CUDA(cudaMemset(ws->dbg, 0, sizeof(long long) * 8));
     CFLX_CUDA(cudaMemset(ws->slot_hdr, 0, sizeof(uint2) * 2 * MAXG * 4));
     CFLX_CUDA(cudaMemset(ws->slot_rows, 0, sizeof(uint2) * 2 * MAXG * 64));
+    // column-owner kernel for panels of <= 1024 rows: per-block flags, pivot positions, the CTA ticket
+    CFLX_CUDA(cudaMalloc(&ws->sk_flags, sizeof(unsigned) * 1024));
+    CFLX_CUDA(cudaMalloc(&ws->sk_ppos, sizeof(int) * 16384));
+    CFLX_CUDA(cudaMalloc(&ws->sk_ticket, sizeof(unsigned)));
+    CFLX_CUDA(cudaMemset(ws->sk_flags, 0, sizeof(unsigned) * 1024));
+    CFLX_CUDA(cudaMemset(ws->sk_ticket, 0, sizeof(unsigned)));
+    ws->sk_epoch = 0;
+    ws->sk_ticket_count = 0;
+    {
+        const char* e = getenv("CFLX_STACK_KERNEL");  // 0 = keep the row-owner kernel for small panels too
+        ws->sk_enabled = e ? atoi(e) : 1;
+    }
     return CFLX_OK;
 }
 void panel_workspace_destroy(PanelWorkspace* ws) {
     cudaFree(ws->slot_hdr);
     cudaFree(ws->dbg);
     cudaFree(ws->slot_rows);
+    cudaFree(ws->sk_flags);
+    cudaFree(ws->sk_ppos);
+    cudaFree(ws->sk_ticket);
     *ws = PanelWorkspace{};
 }
 
@@ -634,6 +843,11 @@ void panel_workspace_destroy(PanelWorkspace* ws) {
 int launch_panel_getrf_a00(double* W, int64_t ldw, int n, int v, int* perm_out, double* A00, int* nb_used,
                            PanelWorkspace* ws, cudaStream_t stream) {
     if (v <= 0 || n < 0) return CFLX_ERR_ARG;
+    if (ws->sk_enabled && n >= v && n <= 1024 && v % SK_CB == 0 && v <= 16384 && ldw % 2 == 0 &&
+        (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+        if (nb_used) *nb_used = 0;  // nothing emitted into A00: launch_gather_a00 takes every entry from W
+        return launch_stack_getrf(W, ldw, n, v, perm_out, ws, stream);
+    }
     PanelArgs a{};
     a.W = W;
     a.ldw = ldw;

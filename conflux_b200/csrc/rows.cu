@@ -66,7 +66,7 @@ __global__ void gather_a00_kernel(const double* __restrict__ W, int64_t ldw, con
     if (e >= (int64_t)v * v) return;
     const int i = (int)(e / v), c = (int)(e % v);
     double val;
-    if (c < (i / nb) * nb) {
+    if (nb <= 0 || c < (i / nb) * nb) {  // nb <= 0: the search kernel emitted nothing, every entry comes from W
         val = W[(int64_t)c * ldw + perm[i]];
         A00[e] = val;
     } else {

@@ -74,6 +74,12 @@ int cflx_lu_create(cflx_comm*, int M, int N, int v, int Px, int Py, int Pz, cflx
 int cflx_lu_info(const cflx_lu*, int* info_out);
 /* host -> device copy of this rank's local matrix (conflux tile layout, row-major, ld = Nl); kept pristine */
 int cflx_lu_set_local(cflx_lu*, const double* host_local);
+/* Input streaming for back-to-back factorisations (no counterpart in the reference, whose input already sits in host
+ * memory): the NEXT cflx_lu_factor uploads `host_next` (page-locked; free again when that call returns) into the input
+ * buffer behind its own working copy, on a copy stream, so the transfer overlaps the factorisation; the factorisation
+ * after that consumes it without a cflx_lu_set_local.  cflx_lu_validate of a run whose input buffer was handed on is
+ * refused (CFLX_ERR_STATE). */
+int cflx_lu_queue_next_local(cflx_lu*, const double* host_next);
 /* COLLECTIVE.  Runs steps 0..Nt-1 on the GPU(s).  ms_out = device time of the main loop only (CUDA events on
  * this rank's stream, after a grid barrier) -- the region the reference times (conflux_opt.hpp:531-532,1805). */
 int cflx_lu_factor(cflx_lu*, double* ms_out);

@@ -46,6 +46,26 @@ def test_panel_getrf_integer_ties():
         _check_panel(rng.integers(0, 4, size=(n, v)).astype(np.float64) + np.eye(n, v) * 0.0)
 
 
+@pytest.mark.parametrize("n,v", [(1024, 512), (512, 256), (256, 128), (700, 512), (1000, 16), (96, 32), (512, 512)])
+def test_column_owner_kernel_is_bit_identical_to_the_row_owner_kernel(n, v, monkeypatch):
+    """Panels of <= 1024 rows (the 2v x v tournament stacks) run on stack_getrf_kernel (one CTA per 16 columns, no
+    exchange per column); its fma chains are those of panel_getrf_kernel, so pivots AND factors must agree bit for bit."""
+    rng = np.random.default_rng(n * 7 + v)
+    for P in (rng.standard_normal((n, v)), rng.integers(-3, 4, size=(n, v)).astype(np.float64)):
+        monkeypatch.setenv("CFLX_STACK_KERNEL", "1")
+        perm1, A1, LU1, _ = cb.dbg.panel(P)
+        monkeypatch.setenv("CFLX_STACK_KERNEL", "0")
+        perm0, A0, LU0, _ = cb.dbg.panel(P)
+        assert np.array_equal(perm1, perm0)
+        assert np.array_equal(A1, A0)                      # L00\\U00 of the winners, every bit
+        # the factored panel: multipliers of every row (the row-owner kernel never writes the U part of a pivot row back)
+        rest = np.setdiff1d(np.arange(n), perm1)
+        assert np.array_equal(LU1[rest], LU0[rest])
+        low = np.tril_indices(v, -1)
+        assert np.array_equal(LU1[perm1][low], LU0[perm0][low])
+        assert np.array_equal(np.triu(LU1[perm1]), np.triu(A1))   # and the column-owner kernel leaves L\\U in place
+
+
 def test_panel_getrf_fewer_rows_than_columns():
     rng = np.random.default_rng(5)
     for (n, v) in [(3, 8), (1, 4), (10, 32), (0, 8)]:
