@@ -171,6 +171,86 @@ __global__ void __launch_bounds__(1024) potrf_tile_kernel(double* __restrict__ D
     if (t == 0 && s_bad) info[0] = s_bad;
 }
 
+// Cholesky of ONE 128 x 128 diagonal block held entirely in shared memory (the building block of potrf_tile): all 512
+// threads take part in every phase -- 32-column diagonal blocks on warp 0 (row per lane), the rows below
+// by forward substitution (one row per thread), the trailing part one element per thread from shared memory.  D / UT are
+// windows of the tile (leading dimensions ldd / ldu), Uc a contiguous copy of L^T for the block-column solve.
+constexpr int QBK = 128;
+constexpr int QPITCH = QBK + 1;
+constexpr int QTHREADS = 512;
+__global__ void __launch_bounds__(QTHREADS) potrf128_kernel(double* __restrict__ D, int ldd, double* __restrict__ UT, int ldu,
+                                                        double* __restrict__ Uc, int* __restrict__ info, int col_off) {
+    extern __shared__ double As[];  // [QBK][QPITCH], lower triangle
+    __shared__ int s_bad;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) s_bad = 0;
+    for (int e = t; e < QBK * QBK; e += QTHREADS) {
+        const int r = e / QBK, c = e % QBK;
+        As[r * QPITCH + c] = (c <= r) ? D[(size_t)r * ldd + c] : 0.0;
+    }
+    __syncthreads();
+    for (int jb = 0; jb < QBK; jb += PB) {
+        const int m = QBK - jb - PB;
+        if (warp == 0) {  // 32 x 32 diagonal block in place, lane = row (shared memory: a register array of 32 doubles that is
+                          // indexed by the unrolled column loop ends up in local memory, which is what made the old kernel slow)
+            double* B = As + jb * QPITCH + jb;
+            for (int c = 0; c < PB; ++c) {
+                const double d = B[c * QPITCH + c];
+                if (!(d > 0.0) && lane == 0 && s_bad == 0) s_bad = col_off + jb + c + 1;
+                const double sq = sqrt(d);
+                double l = 0.0;
+                if (lane == c) B[c * QPITCH + c] = sq;
+                else if (lane > c) {
+                    l = B[lane * QPITCH + c] / sq;
+                    B[lane * QPITCH + c] = l;
+                }
+                __syncwarp();
+#pragma unroll 4
+                for (int c2 = c + 1; c2 < PB; ++c2) {
+                    const double l2 = B[c2 * QPITCH + c];  // L[c2][c], broadcast
+                    if (lane >= c2) B[lane * QPITCH + c2] = fma(-l, l2, B[lane * QPITCH + c2]);
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (m <= 0) break;
+        // rows below: X = P * L_d^-T, one row per thread, in place in shared memory (L_d is a broadcast read)
+        if (t < m) {
+            double* prow = As + (jb + PB + t) * QPITCH + jb;
+            const double* Ld = As + jb * QPITCH + jb;
+#pragma unroll 4
+            for (int c = 0; c < PB; ++c) {
+                double sacc = prow[c];
+                for (int q = 0; q < c; ++q) sacc = fma(-prow[q], Ld[c * QPITCH + q], sacc);
+                prow[c] = sacc / Ld[c * QPITCH + c];
+            }
+        }
+        __syncthreads();
+        // trailing part (lower triangle): T[i][k] -= X[i][:] . X[k][:], one element per thread and pass
+        for (int e = t; e < m * m; e += QTHREADS) {
+            const int i = e / m, k = e % m;
+            if (k > i) continue;
+            const double* xi = As + (jb + PB + i) * QPITCH + jb;
+            const double* xk = As + (jb + PB + k) * QPITCH + jb;
+            double sacc = 0.0;
+#pragma unroll
+            for (int c = 0; c < PB; ++c) sacc = fma(xi[c], xk[c], sacc);
+            As[(jb + PB + i) * QPITCH + jb + PB + k] -= sacc;
+        }
+        __syncthreads();
+    }
+    // L into the tile (zeros above its diagonal), L^T into UT and into the contiguous copy
+    for (int e = t; e < QBK * QBK; e += QTHREADS) {
+        const int r = e / QBK, c = e % QBK;
+        D[(size_t)r * ldd + c] = As[r * QPITCH + c];            // (zeros above the diagonal were loaded as zeros)
+        const double lt = As[c * QPITCH + r];                    // L^T[r][c] = L[c][r]
+        UT[(size_t)r * ldu + c] = lt;
+        Uc[e] = lt;
+    }
+    if (t == 0 && s_bad) info[0] = s_bad;
+}
+
 // zeros above the diagonal of D (= L) and below the diagonal of UT (= L^T)
 __global__ void tri_clean_kernel(double* __restrict__ D, double* __restrict__ UT, int v) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -403,11 +483,11 @@ int potrf_tile(cflx_chol* ch, size_t psm, cudaStream_t s) {
     double* Li = Ui + QB * QB;                 // [QB][QB]  (unit-lower companion of launch_diag_inverses, unused)
     double* XT0 = Li + QB * QB;                // [QB][v]   block column below the diagonal block, transposed
     double* XT = XT0 + (size_t)QB * v;         // [QB][v]   ... after the solve
-    const size_t psm_q = ((size_t)PB * (PB + 1) + (size_t)QB * (PB + 1)) * sizeof(double);
+    static_assert(QB == QBK, "block width of the tile Cholesky");
     for (int jb = 0; jb < v; jb += QB) {
         const int m = v - jb - QB;
-        potrf_tile_kernel<<<1, 1024, psm_q, s>>>(ch->D + (size_t)jb * v + jb, QB, v, ch->A00 + (size_t)jb * v + jb, v, U128,
-                                                 ch->info + 1, jb);
+        potrf128_kernel<<<1, QTHREADS, QBK * QPITCH * sizeof(double), s>>>(ch->D + (size_t)jb * v + jb, v, ch->A00 + (size_t)jb * v + jb, v,
+                                                                        U128, ch->info + 1, jb);
         CFLX_CUDA(cudaGetLastError());
         ch->launches++;
         if (m <= 0) break;
@@ -627,6 +707,7 @@ int cflx_chol_create(cflx_comm* c, int N, int v, int Px, int Py, int Pz, cflx_ch
     }
     const size_t psm = ((size_t)PB * (PB + 1) + (size_t)v * (PB + 1)) * sizeof(double);
     if (cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm) != cudaSuccess) return fail(CFLX_ERR_CUDA);
+    if (cudaFuncSetAttribute(potrf128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(QBK * QPITCH * sizeof(double))) != cudaSuccess) return fail(CFLX_ERR_CUDA);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(CFLX_ERR_CUDA);
     *out = ch;
     return CFLX_OK;

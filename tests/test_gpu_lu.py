@@ -114,6 +114,41 @@ def test_repeat_is_deterministic_and_input_untouched():
     assert np.array_equal(a["perm"], b["perm"]) and np.array_equal(a["C"][0], b["C"][0])
 
 
+def test_streamed_input_factors_the_matrix_the_previous_call_uploaded():
+    """cflx_lu_queue_next_local / LU_rep(next_data=...): the upload of matrix i+1 overlaps factorisation i; each
+    factorisation must see exactly its own matrix, and the residual of a run whose input buffer was handed on is refused."""
+    import conflux_b200 as cb
+    comm = cb.Comm(1, 0, None, 0)
+    gv = cb.lu_params(1024, 1024, 128, 1, 1, 1, comm)
+    rng = np.random.default_rng(11)
+    mats = [cb.pinned_empty((gv.Ml, gv.Nl)) for _ in range(3)]
+    for m in mats:
+        m[...] = rng.standard_normal((gv.Ml, gv.Nl))
+    want = []
+    for m in mats:                                  # one at a time, synchronous upload
+        gv.data = m
+        perm, C = np.zeros(gv.M, dtype=np.int32), np.zeros((gv.Ml, gv.Nl))
+        cb.LU_rep(gv, C, perm)
+        want.append((perm, C))
+    assert not np.array_equal(want[0][0], want[1][0])
+    gv.data = mats[0]
+    got = []
+    for i in range(3):                              # streamed: matrix i+1 travels while matrix i is factored
+        perm, C = np.zeros(gv.M, dtype=np.int32), np.zeros((gv.Ml, gv.Nl))
+        cb.LU_rep(gv, C, perm, upload=(i == 0), next_data=mats[i + 1] if i < 2 else None)
+        got.append((perm, C))
+        if i < 2:
+            with pytest.raises(cb.ConfluxError):
+                cb.residual(gv)                     # the input buffer already belongs to matrix i+1
+    for (p0, c0), (p1, c1) in zip(want, got):
+        assert np.array_equal(p0, p1) and np.array_equal(c0, c1)
+    assert cb.residual(gv) <= RESIDUAL_TOL           # the last run kept its input
+    for m in mats:
+        cb.pinned_free(m)
+    gv.free_comms()
+    comm.close()
+
+
 GRIDS = [(64, 8, 2, 2, 1), (128, 16, 1, 1, 2), (128, 8, 2, 2, 2), (512, 32, 2, 2, 1), (512, 64, 2, 2, 2),
          (1024, 128, 1, 1, 2)]
 
