@@ -399,6 +399,18 @@ int broadcast_pieces(cflx_chol* ch, int t, int gfirst, int jmin, int buf, cudaSt
 }
 // X[i][j] -= L[i][t] * L[j][t]^T on the local tiles with global tile row i >= tile column j, j in the local column tiles
 // [lj_lo, lj_hi) (global index >= jmin; lower triangle), each z layer with its own slab of the v contraction indices.
+// SMs the persistent tcgen05 update leaves to the look-ahead panel pipeline on the side stream (CFLX_CHOL_LEAVE)
+static int chol_leave_sms() {
+    static int leave = -1;
+    if (leave < 0) {
+        const char* e = getenv("CFLX_CHOL_LEAVE");
+        leave = e ? atoi(e) : 8;
+        if (leave < 0) leave = 0;
+        if (leave > 100) leave = 100;
+    }
+    return leave;
+}
+
 int update_columns(cflx_chol* ch, int gfirst, int jmin, int buf, double* X, int lj_lo, int lj_hi, cudaStream_t s, int planes_buf = -1) {
     const int v = ch->v, Px = ch->Px, Py = ch->Py, Ml = ch->Ml, Nl = ch->Nl;
     const int pi = ch->pi, pj = ch->pj, pk = ch->pk;
@@ -432,7 +444,7 @@ int update_columns(cflx_chol* ch, int gfirst, int jmin, int buf, double* X, int 
         g.ldd = Nl;
         g.alpha = -1.0; g.beta = 1.0;
         if (ch->use_ozaki && planes_buf == buf)   // planes of this buffer set are current (see split_planes)
-            CFLX_TRY(launch_ozaki_gemm(&ch->oz, M, g.N, (li - my_first) * v, (lj - lj0) * v, g.D, Nl, ch->oz.sms - 8, s));
+            CFLX_TRY(launch_ozaki_gemm(&ch->oz, M, g.N, (li - my_first) * v, (lj - lj0) * v, g.D, Nl, ch->oz.sms - chol_leave_sms(), s));
         else
             CFLX_TRY(launch_gemm_tn(g, s));
         ch->launches++;

@@ -756,7 +756,7 @@ int cflx_lu_create(cflx_comm* c, int M, int N, int v, int Px, int Py, int Pz, cf
             if (cudaEventCreateWithFlags(&lu->ev_fork, cudaEventDisableTiming) != cudaSuccess) return fail(CFLX_ERR_CUDA);
             if (cudaEventCreateWithFlags(&lu->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail(CFLX_ERR_CUDA);
             const char* c = getenv("CFLX_PANEL_CTAS");
-            lu->pws.cta_cap = c ? atoi(c) : (lu->P == 1 ? 32 : 48);
+            lu->pws.cta_cap = c ? atoi(c) : (lu->P == 1 ? 32 : 64);  // measured at 2x2x1 (C3): 48 -> 308 ms, 64 -> 283 ms, 96 -> 309 ms
         }
     }
     // zero the panels once: padded columns are read (and masked) by the GEMM producer

@@ -20,7 +20,8 @@ def launches(src, dst):
     for row in csv.DictReader(lines):
         val = float(row["Metric Value"].replace(",", "")) * scale.get(row["Metric Unit"], 1.0)
         name = re.sub(r"^void ", "", row["Kernel Name"])
-        name = re.sub(r"\(.*", "", name).replace("cflx::<unnamed>::", "").replace("unnamed>::", "")
+        name = name.replace("cflx::<unnamed>::", "").replace("<unnamed>::", "").replace("unnamed>::", "")
+        name = re.sub(r"\(.*", "", name)
         name = re.sub(r"<.*", "", name)
         if row["Metric Name"].startswith("gpu__time_duration"):
             tot[name] += val
