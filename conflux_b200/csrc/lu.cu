@@ -756,7 +756,9 @@ int cflx_lu_create(cflx_comm* c, int M, int N, int v, int Px, int Py, int Pz, cf
             if (cudaEventCreateWithFlags(&lu->ev_fork, cudaEventDisableTiming) != cudaSuccess) return fail(CFLX_ERR_CUDA);
             if (cudaEventCreateWithFlags(&lu->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail(CFLX_ERR_CUDA);
             const char* c = getenv("CFLX_PANEL_CTAS");
-            lu->pws.cta_cap = c ? atoi(c) : (lu->P == 1 ? 32 : 64);  // measured at 2x2x1 (C3): 48 -> 308 ms, 64 -> 283 ms, 96 -> 309 ms
+            // measured: 1x1x1 (C2) 32 -> 96.9 ms, 48 -> 96.7, 64 -> 102.6; 2x2x1 (C3) 48 -> 308 ms, 64 -> 283, 96 -> 309;
+            // 1x1x2 was measured at 48 only (no tournament there, the trailing update is twice as large per rank)
+            lu->pws.cta_cap = c ? atoi(c) : (lu->P == 1 ? 32 : (lu->Px == 1 ? 48 : 64));
         }
     }
     // zero the panels once: padded columns are read (and masked) by the GEMM producer
