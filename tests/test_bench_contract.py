@@ -41,3 +41,27 @@ def test_bench_golden_pivots_present():
         g = bench.load_golden_perm(N, v, grid)
         assert g is not None and sorted(np.asarray(g).tolist()) == list(range(N))
     assert bench.load_golden_perm(65536, 512, (2, 2, 2)) is None
+
+
+def test_reference_arm_prints_the_contract_line_on_a_small_override():
+    """`bench.py --impl reference` end to end (size override, a few seconds): one JSON line with impl/metric/config/
+    cpu_baseline/e2e, timed inside ONE child process; also guards the threading set-up of that child (OMP_PROC_BIND made
+    OpenBLAS' threads inherit a one-CPU mask: 40x slower)."""
+    import subprocess
+    import sys
+    import time
+    import pytest
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    t0 = time.time()
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1",
+                          "--warmup", "0", "--N", "1024", "--v", "128"], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, CFLX_REF_BUDGET_S="5"))
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and "unavailable" not in line, line
+    assert line["metric"].startswith("LU GFLOP/s") and line["unit"] == "GFLOP/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "size override" in line["config"]["workload"] and line["steps_done"] == 1
+    assert time.time() - t0 < 120
