@@ -99,9 +99,10 @@ try:                                      # pin the whole process (BLAS pthreads
     import time                           # that are idle right now: the box is shared, the first CPUs usually are not
     allowed = sorted(os.sched_getaffinity(0))
     a = _busy(); time.sleep(0.5); b = _busy()
-    load = {c: (b[c][0] - a[c][0]) / max(1, b[c][1] - a[c][1]) for c in allowed if c in a and c in b}
-    cpus = sorted(sorted(load, key=lambda c: (round(load[c], 1), c))[:cores]) or allowed[:cores]
-    os.sched_setaffinity(0, cpus)
+    load = [(b[c][0] - a[c][0]) / max(1, b[c][1] - a[c][1]) if c in a and c in b else 1.0 for c in allowed]
+    k = min(cores, len(allowed))          # the least-loaded window of CONSECUTIVE CPUs (one socket / NUMA node as a rule)
+    best = min(range(len(allowed) - k + 1), key=lambda i: (round(sum(load[i:i + k]), 1), i))
+    os.sched_setaffinity(0, allowed[best:best + k])
 except Exception:
     pass
 sys.path.insert(0, %(root)r)
